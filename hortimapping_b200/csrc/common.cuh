@@ -1,0 +1,119 @@
+// Shared declarations of the hortimapping_b200 CUDA library (internal; the public ABI is
+// include/hortimapping_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hortimapping_b200.h"
+
+#define HM_SKIP_COL 477   // lin3 output width = 512 - 35 (deep_sdf_decoder.py:41-42): columns 477..511 of
+                          // the layer-4 input carry the raw [latent, xyz] vector (deep_sdf_decoder.py:87-88)
+
+void hm_set_error(const char* fmt, ...);
+
+#define HM_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      hm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return HM_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define HM_CHECK(cond, ...)          \
+  do {                               \
+    if (!(cond)) {                   \
+      hm_set_error(__VA_ARGS__);     \
+      return HM_ERR_INVALID;         \
+    }                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core engine: operator list of one tile pass.  An "op" is one fused layer GEMM
+//   D[64 x N] = A[64 x K] * W_op^T  (fp16 hi/lo split operands, fp32 accumulate in TMEM).
+// Forward ops F0..F7 are lin0..lin7; backward ops B7..B0 multiply by the transposed weights.
+// ---------------------------------------------------------------------------------------------
+#define HM_TC_NOPS_FWD 8
+#define HM_TC_NOPS_ALL 16
+#define HM_TC_TILE_M 64          // rows (points) per tile
+#define HM_TC_STAGE_N 128        // weight rows (output features) per pipeline stage
+#define HM_TC_CHUNK_K 64         // K extent of one 128-byte swizzle atom row (fp16)
+
+struct hm_tc_op {
+  int32_t n_kchunks;             // K / 64 of the A operand (1 for F0, 8 otherwise)
+  int32_t n_nblocks;             // N / 128 (4; 1 for B0 whose stage holds 64 rows)
+  int32_t stage_rows;            // weight rows per stage (128; 64 for B0)
+  int32_t pad_;
+  float in_scale;                // power of two applied to the A operand before the fp16 split
+  float out_unscale;             // 1 / (in_scale * w_scale): turns the accumulator back into fp32 units
+  int64_t blob_offset;           // byte offset of this op's first stage in the weight blob
+};
+
+struct hm_tc_plan {
+  hm_tc_op ops[HM_TC_NOPS_ALL];
+};
+
+struct hm_context {
+  int device = 0;
+  int engine = HM_ENGINE_TC;
+  int sm_count = 0;
+  // fp32 weights (device): W[l] is [out_pad][in] with lin3 zero-padded to 512 rows
+  float* d_W[HM_LAYERS] = {};
+  float* d_b[HM_LAYERS] = {};
+  int in_dim[HM_LAYERS] = {};
+  int out_dim[HM_LAYERS] = {};     // padded (lin3 -> 512)
+  std::vector<float> h_W[HM_LAYERS];
+  std::vector<float> h_b[HM_LAYERS];
+  // tensor-core engine
+  uint8_t* d_tc_blob = nullptr;    // pre-swizzled fp16 hi/lo weight stages for all 16 ops
+  size_t tc_blob_bytes = 0;
+  hm_tc_plan tc_plan;
+  float act_absmax[HM_TC_NOPS_ALL] = {};   // calibration result: max |A operand| per op
+  float* d_tc_bias = nullptr;      // [8][512] biases of lin0..7 (lin3 padded with 0)
+  float* d_w8 = nullptr;           // [512] lin8 weight, d_b8 scalar in d_b[8]
+  uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
+  int32_t* d_tc_flags = nullptr;   // saturation counter etc.
+  // grow-only workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* ws2 = nullptr;             // optimiser workspace (separate so decoder calls never alias it)
+  size_t ws2_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  hm_counters counters = {};
+  // last LM system (test hook)
+  float* d_last_H = nullptr;
+  float* d_last_b = nullptr;
+  float* d_last_dx = nullptr;
+  int last_est = 0;
+  int last_n_fruits = 0;
+};
+
+int hm_ws_reserve(hm_context* ctx, size_t bytes);     // ctx->ws
+int hm_ws2_reserve(hm_context* ctx, size_t bytes);    // ctx->ws2
+
+// ---- decoder engines (decoder_simt.cu / decoder_tc.cu) ----
+// Rows are described by xyz [n][3] + a latent table [L][32] + optional per-row latent index (NULL = all
+// rows use latent 0), or by full rows [n][35] (d_rows != NULL takes precedence).
+struct hm_rows {
+  const float* d_rows;       // [n][35] or NULL
+  const float* d_xyz;        // [n][3]
+  const float* d_latents;    // [L][32]
+  const int32_t* d_row_latent;  // [n] or NULL
+  int64_t n;
+  const int32_t* d_n_dynamic;   // optional device-side row count (<= n); NULL = use n
+};
+
+int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st,
+                   float* h_absmax_out /* [16] or NULL: calibration */);
+int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st);
+int hm_tc_init(hm_context* ctx);          // build weight blob + plan from ctx->h_W and act_absmax
+void hm_tc_free(hm_context* ctx);
+int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st);
+
+// ---- optimiser (optimizer.cu) ----
+int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* b, bool joint, cudaStream_t st);

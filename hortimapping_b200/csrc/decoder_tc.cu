@@ -1,0 +1,659 @@
+// Tensor-core decoder engine (HM_ENGINE_TC): the whole DeepSDF MLP -- forward and, optionally, the
+// input gradient -- for a tile of 64 query rows in ONE persistent, warp-specialised sm_100a kernel.
+//
+// Restates deepsdf/networks/deep_sdf_decoder.py:75-110 (forward) and the autograd input gradient of
+// wild_completion/utils.py:112-122,175-193.
+//
+//   * every layer is a tcgen05.mma GEMM  D[64 x 512] (+)= A[64 x K] * W^T  with fp32 accumulators in
+//     TMEM.  fp32 parity needs more than one fp16/bf16 MMA: operands are split
+//     x*s = hi + lo (fp16 each, s a calibrated power of two) and three MMAs hi*hi + lo*hi + hi*lo are
+//     accumulated -- measured 3e-8 abs SDF error on the shipped decoder, i.e. fp32 grade.
+//   * activations never leave the SM: the epilogue warps read the accumulator from TMEM, apply
+//     bias/ReLU (or the ReLU mask in the backward pass), re-split to fp16 hi/lo and write the next
+//     layer's A operand straight into shared memory in the 128-byte-swizzled K-major UMMA layout.
+//     The next layer's MMAs start per 128-column slice as soon as that slice of A is written, into
+//     the other half of TMEM (two 256-column accumulators; the 64x512 tile is folded onto the 128
+//     TMEM lanes as 2 x (64 rows x 256 columns)).
+//   * weights (pre-split, pre-scaled, pre-swizzled on the host into 32 KB stage blobs in the exact
+//     order the MMA warp consumes them) stream L2 -> shared memory with cp.async.bulk + mbarrier
+//     complete_tx through a 3-stage ring.
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (+ TMEM alloc),
+// warps 2..5 = epilogue (one per TMEM sub-partition).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;                 // 128 rows x 64 k x 2 B x {hi, lo}
+constexpr int kTileBytes = 16384;                  // one 128 x 64 fp16 tile
+constexpr int kAChunkBytes = 8192;                 // 64 rows x 64 k x 2 B
+constexpr int kSmemAHi = 0;
+constexpr int kSmemALo = 65536;
+constexpr int kSmemStages = 131072;
+constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;   // 229376
+constexpr int kSmemTotal = kSmemBars + 256;
+constexpr int kThreads = 192;
+constexpr int kMaskWordsPerOp = 64 * 16;           // 64 rows x 512 bits
+
+// barrier slots (8 bytes each) inside the barrier block
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_ACC_FULL = 10, BAR_COUNT = 12 };
+
+struct TcParams {
+  hm_tc_plan plan;
+  const uint8_t* blob;
+  const float* bias;          // [8][512]
+  const float* w8;            // [512]
+  const float* b8;            // [1]
+  const float* rows;          // [n][35] or null
+  const float* xyz;           // [n][3]
+  const float* latents;       // [L][32]
+  const int32_t* row_latent;  // [n] or null
+  const int32_t* n_dynamic;   // device row count or null
+  int64_t n;
+  float* sdf;
+  float* jac;
+  uint32_t* masks;            // [grid][8][64][16]
+  int32_t* flags;             // [0] = saturation count
+  float b0_in_scale_dummy;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, issued by one thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address
+// bits [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major), SBO [32,46) = 1024 B (8 rows x 128 B),
+// version [46,48) = 1 (Blackwell), layout_type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format F16 (0),
+// K-major A and B, n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (row, k) of a K-major SW128 tile whose rows are 64 fp16 (128 B) wide
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+// split 8 consecutive fp32 values (already scaled) into fp16 hi / lo and return them packed for one
+// 16-byte store each.  hi = rn(x) saturated to the finite fp16 range, lo = rn(x - hi).
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, int& sat) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a = x[2 * i], b = x[2 * i + 1];
+    float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+    sat |= (ac != a) | (bc != b);
+    __half2 hh = __floats2half2_rn(ac, bc);
+    float2 hf = __half22float2(hh);
+    __half2 ll = __floats2half2_rn(ac - hf.x, bc - hf.y);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// write 32 consecutive columns (local k0 .. k0+31 of chunk `chunk`) of row `row` of the A operand
+__device__ __forceinline__ void store_a32(uint8_t* smem, int chunk, int row, int k0, const float* x, int& sat) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 hi, lo;
+    split8(x + 8 * u, hi, lo, sat);
+    uint32_t off = (uint32_t)chunk * kAChunkBytes + sw128_offset(row, k0 + 8 * u);
+    *reinterpret_cast<uint4*>(smem + kSmemAHi + off) = hi;
+    *reinterpret_cast<uint4*>(smem + kSmemALo + off) = lo;
+  }
+}
+
+// k-chunk consumption order of an 8-chunk op: pairs (p, p+4) become ready together (the two column
+// halves of the epilogue), so the MMA warp walks 0,4,1,5,2,6,3,7.
+__host__ __device__ __forceinline__ int chunk_of(int pair, int which) { return pair + 4 * which; }
+
+template <bool kJac>
+__global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + kSmemBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
+  constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
+    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), 4);
+    for (int b = 0; b < 2; ++b) mbar_init(bar(BAR_ACC_FULL + b), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
+  const int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int op = 0; op < kOps; ++op) {
+          const hm_tc_op& o = P.plan.ops[op];
+          const uint32_t bytes = (uint32_t)o.stage_rows * 128u * 2u;
+          const int nst = o.n_kchunks * o.n_nblocks;
+          const uint8_t* src = P.blob + o.blob_offset;
+          for (int s = 0; s < nst; ++s) {
+            mbar_wait(bar(BAR_W_EMPTY + slot), phase ^ 1);
+            mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+            bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes, bytes, bar(BAR_W_FULL + slot));
+            if (++slot == kStages) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, op_seq = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int op = 0; op < kOps; ++op, ++op_seq) {
+          const hm_tc_op& o = P.plan.ops[op];
+          const uint32_t buf = op_seq & 1;
+          const uint32_t idesc = make_idesc(HM_TC_TILE_M, o.stage_rows);
+          const uint32_t lo_off = (uint32_t)o.stage_rows * 128u;     // lo tile follows the hi tile inside a stage
+          bool first_k = true;
+          for (int pair = 0; pair < 4; ++pair) {
+            mbar_wait(bar(BAR_A_READY + pair), op_seq & 1);
+            tc_fence_after();
+            const int nwhich = (o.n_kchunks == 1) ? (pair == 0 ? 1 : 0) : 2;
+            for (int which = 0; which < nwhich; ++which) {
+              const int chunk = chunk_of(pair, which);
+              const uint32_t a_hi = smem_base + kSmemAHi + chunk * kAChunkBytes;
+              const uint32_t a_lo = smem_base + kSmemALo + chunk * kAChunkBytes;
+              for (int nb = 0; nb < o.n_nblocks; ++nb) {
+                mbar_wait(bar(BAR_W_FULL + slot), phase);
+                tc_fence_after();
+                const uint32_t w_hi = smem_base + kSmemStages + slot * kStageBytes;
+                const uint32_t w_lo = w_hi + lo_off;
+                const uint32_t d = tmem_base + ((uint32_t)(16 * (nb >> 1)) << 16) + buf * 256 + (nb & 1) * 128;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
+                  const uint64_t dwh = make_desc(w_hi + ks * 32), dwl = make_desc(w_lo + ks * 32);
+                  umma_f16(d, dah, dwh, idesc, (first_k && ks == 0) ? 0u : 1u);
+                  umma_f16(d, dal, dwh, idesc, 1u);
+                  umma_f16(d, dah, dwl, idesc, 1u);
+                }
+                umma_commit(bar(BAR_W_EMPTY + slot));
+                if (++slot == kStages) { slot = 0; phase ^= 1; }
+              }
+              first_k = false;
+            }
+          }
+          umma_commit(bar(BAR_ACC_FULL + buf));
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int sp = warp & 3;                 // TMEM sub-partition this warp may read
+    const int half = lane >> 4;              // which 256-column half of the 512-wide tile this thread owns
+    const int row = 16 * sp + (lane & 15);   // tile row (M = 64 layout: row r <-> lane 32*(r/16) + r%16)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
+    uint32_t* my_masks = P.masks + (size_t)blockIdx.x * 8 * kMaskWordsPerOp + row * 16 + half * 8;
+    uint32_t op_seq = 0;
+    int sat = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t grow = tile * HM_TC_TILE_M + row;
+      const bool row_ok = grow < n_rows;
+      const int64_t lrow = row_ok ? grow : (n_rows - 1);
+      // raw input x0 = [latent(32), xyz(3)] of this row (deep_sdf_decoder.py:76-88)
+      const float* lat_src;
+      const float* xyz_src;
+      if (P.rows) { lat_src = P.rows + lrow * HM_IN; xyz_src = lat_src + HM_LATENT; }
+      else { lat_src = P.latents + (size_t)(P.row_latent ? P.row_latent[lrow] : 0) * HM_LATENT; xyz_src = P.xyz + lrow * 3; }
+      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64)
+      {
+        const float s0 = P.plan.ops[0].in_scale;
+        float x[32];
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = lat_src[i] * s0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = (i < 3) ? xyz_src[i] * s0 : 0.f;
+        }
+        store_a32(smem, 0, row, 32 * half, x, sat);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) for (int p = 0; p < 4; ++p) mbar_arrive(bar(BAR_A_READY + p));
+      }
+      float skip[3 + 32];                      // d sdf / d x0 through the skip connection (half 1 threads)
+      float f_sdf = 0.f;
+#pragma unroll 1
+      for (int op = 0; op < kOps; ++op, ++op_seq) {
+        const uint32_t buf = op_seq & 1;
+        const hm_tc_op& o = P.plan.ops[op];
+        const float unscale = o.out_unscale;
+        const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
+        mbar_wait(bar(BAR_ACC_FULL + buf), (op_seq >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = t_lane + buf * 256;
+        if (op < 7) {
+          // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next
+          const float* bias = P.bias + op * HM_HIDDEN + 256 * half;
+          const float k_mul = unscale * s_next;
+          uint32_t* mrow = my_masks + op * kMaskWordsPerOp;
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+              const int lc = p * 64 + j * 32;
+              float v[32];
+              tmem_ld32(t_acc + lc, v);
+              uint32_t m = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float y = fmaf(v[i], k_mul, __ldg(bias + lc + i) * s_next);
+                m |= (y > 0.f ? 1u : 0u) << i;
+                v[i] = fmaxf(y, 0.f);
+              }
+              if (op == 3) {
+                // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
+                const int gc0 = 256 * half + lc;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int gc = gc0 + i;
+                  if (gc >= HM_SKIP_COL) {
+                    const int k = gc - HM_SKIP_COL;
+                    v[i] = (k < HM_LATENT ? lat_src[k] : xyz_src[k - HM_LATENT]) * s_next;
+                    m &= ~(1u << i);
+                  }
+                }
+              }
+              if (kJac) mrow[p * 2 + j] = m;
+              store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+          }
+        } else if (op == 7) {
+          // ---------------- lin7 epilogue + lin8 + tanh (deep_sdf_decoder.py:107-108)
+          const float* bias = P.bias + 7 * HM_HIDDEN + 256 * half;
+          const float* w8 = P.w8 + 256 * half;
+          uint32_t mk[8];
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float v[32];
+            tmem_ld32(t_acc + q * 32, v);
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float y = fmaf(v[i], unscale, __ldg(bias + q * 32 + i));
+              m |= (y > 0.f ? 1u : 0u) << i;
+              dot = fmaf(fmaxf(y, 0.f), __ldg(w8 + q * 32 + i), dot);
+            }
+            mk[q] = m;
+          }
+          dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+          f_sdf = tanhf(dot + __ldg(P.b8));
+          if (half == 0 && row_ok) P.sdf[grow] = f_sdf;
+          if (kJac) {
+            // d7 = (1 - f^2) * w8 * relu'(h7): A operand of B7
+            const float coef = (1.f - f_sdf * f_sdf) * s_next;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int q = p * 2 + j;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ((mk[q] >> i) & 1u) ? coef * __ldg(w8 + q * 32 + i) : 0.f;
+                store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+              }
+              fence_proxy_async();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+            }
+          } else {
+            tc_fence_before();
+          }
+        } else if (op < 15) {
+          // ---------------- backward through lin_l (l = 15 - op = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
+          const int l = 15 - op;
+          const uint32_t* mrow = my_masks + (l - 1) * kMaskWordsPerOp;
+          const float k_mul = unscale * s_next;
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+              const int lc = p * 64 + j * 32;
+              const uint32_t m = mrow[p * 2 + j];
+              float v[32];
+              tmem_ld32(t_acc + lc, v);
+              if (l == 4 && p == 3) {
+                // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0.
+                // They live in the half-1 lanes: local columns 221..255 = (j=0: i=29..31), (j=1: i=0..31).
+                // (half-0 lanes fill their own copy with values nobody reads.)
+                if (j == 0) {
+                  skip[0] = v[29] * unscale; skip[1] = v[30] * unscale; skip[2] = v[31] * unscale;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) skip[3 + i] = v[i] * unscale;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] * k_mul : 0.f;
+              store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+          }
+        } else {
+          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all in the half-0 lanes) + skip gradient
+          float v0[32], v1[32];
+          tmem_ld32(t_acc, v0);
+          tmem_ld32(t_acc + 32, v1);
+          tc_fence_before();
+          float* jrow = P.jac + grow * HM_IN;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float sk = __shfl_down_sync(0xffffffffu, skip[i], 16);
+            if (half == 0 && row_ok) jrow[i] = fmaf(v0[i], unscale, sk);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float sk = __shfl_down_sync(0xffffffffu, skip[32 + i], 16);
+            if (half == 0 && row_ok) jrow[32 + i] = fmaf(v1[i], unscale, sk);
+          }
+        }
+      }
+    }
+    if (sat) atomicAdd(P.flags, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ bring-up self test
+// One 64 x 128 x 64 GEMM through exactly the building blocks above (SW128 K-major descriptors, M = 64
+// accumulator layout with an optional +16 lane offset, 32x32b TMEM loads); dumps all 128 lanes x 256
+// columns so the host can check the layout assumptions.
+__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
+                                                             float* __restrict__ out, int lane_off, int col_off) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t done_bar;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sa = smem_u32(smem), sb = sa + 8192;
+  for (int i = threadIdx.x; i < 64 * 64; i += 128) *reinterpret_cast<__half*>(smem + sw128_offset(i / 64, i % 64)) = A[i];
+  for (int i = threadIdx.x; i < 128 * 64; i += 128) *reinterpret_cast<__half*>(smem + 8192 + sw128_offset(i / 64, i % 64)) = B[i];
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  // clear the accumulator region we are going to dump
+  {
+    uint32_t z = 0;
+    for (int c = 0; c < 256; ++c)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tb + ((uint32_t)(32 * warp) << 16) + c), "r"(z) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(64, 128);
+    const uint32_t d = tb + ((uint32_t)lane_off << 16) + col_off;
+    for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, ks ? 1u : 0u);
+    umma_commit(smem_u32(&done_bar));
+  }
+  mbar_wait(smem_u32(&done_bar), 0);
+  tc_fence_after();
+  for (int q = 0; q < 8; ++q) {
+    float v[32];
+    tmem_ld32(tb + ((uint32_t)(32 * warp) << 16) + q * 32, v);
+    for (int i = 0; i < 32; ++i) out[(size_t)threadIdx.x * 256 + q * 32 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+// ------------------------------------------------------------------ host side: plan + weight blob
+float pow2_floor(float x) { return std::exp2(std::floor(std::log2(x))); }
+
+__half f2h(float x) { return __float2half_rn(x); }
+
+// Fill one K-major SW128 tile pair (hi then lo) of `rows` x 64 from B(n, k) * scale.
+template <class F>
+void fill_stage(uint8_t* dst, int rows, float scale, F&& get) {
+  uint8_t* hi = dst;
+  uint8_t* lo = dst + (size_t)rows * 128;
+  for (int n = 0; n < rows; ++n)
+    for (int k = 0; k < 64; ++k) {
+      float x = get(n, k) * scale;
+      __half h = f2h(x);
+      __half l = f2h(x - __half2float(h));
+      uint32_t off = sw128_offset(n, k);
+      memcpy(hi + off, &h, 2);
+      memcpy(lo + off, &l, 2);
+    }
+}
+
+}  // namespace
+
+int hm_tc_init(hm_context* ctx) {
+  // op list: F0..F7 (lin0..lin7), B7..B1, B0
+  hm_tc_plan& plan = ctx->tc_plan;
+  std::vector<uint8_t> blob;
+  auto wmax = [&](int l) {
+    float m = 0.f;
+    for (float v : ctx->h_W[l]) m = std::max(m, std::fabs(v));
+    return std::max(m, 1e-20f);
+  };
+  for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
+    const bool fwd = op < 8;
+    const int l = fwd ? op : 15 - op;
+    hm_tc_op& o = plan.ops[op];
+    o.n_kchunks = (op == 0) ? 1 : 8;
+    o.n_nblocks = (op == 15) ? 1 : 4;
+    o.stage_rows = (op == 15) ? 64 : 128;
+    o.pad_ = 0;
+    const float amax = std::max(ctx->act_absmax[op], 1e-20f);
+    o.in_scale = pow2_floor(1024.f / amax);          // 64x headroom below the fp16 maximum
+    const float w_scale = pow2_floor(8192.f / wmax(l));
+    o.out_unscale = 1.f / (o.in_scale * w_scale);
+    o.blob_offset = (int64_t)blob.size();
+    const std::vector<float>& W = ctx->h_W[l];
+    const int in_dim = ctx->in_dim[l];
+    const size_t stage_bytes = (size_t)o.stage_rows * 128 * 2;
+    const int npairs = (o.n_kchunks == 1) ? 1 : 4;
+    for (int pair = 0; pair < npairs; ++pair)
+      for (int which = 0; which < ((o.n_kchunks == 1) ? 1 : 2); ++which) {
+        const int chunk = chunk_of(pair, which);
+        for (int nb = 0; nb < o.n_nblocks; ++nb) {
+          size_t at = blob.size();
+          blob.resize(at + stage_bytes, 0);
+          fill_stage(blob.data() + at, o.stage_rows, w_scale, [&](int n, int k) -> float {
+            const int gn = nb * o.stage_rows + n, gk = chunk * 64 + k;
+            if (fwd) {                       // B[n][k] = W_l[n][k]
+              if (gk >= in_dim) return 0.f;
+              return W[(size_t)gn * in_dim + gk];
+            }
+            // backward: D[row][i] = sum_o d[row][o] W_l[o][i]  ->  B[n = i][k = o] = W_l[o][i]
+            if (gn >= in_dim) return 0.f;
+            return W[(size_t)gk * in_dim + gn];
+          });
+        }
+      }
+  }
+  if (ctx->d_tc_blob && ctx->tc_blob_bytes != blob.size()) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
+  if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size()));
+  ctx->tc_blob_bytes = blob.size();
+  HM_CUDA(cudaMemcpy(ctx->d_tc_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  if (!ctx->d_tc_bias) {
+    HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
+    HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
+    HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 16));
+    HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 16));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  }
+  std::vector<float> bias(8 * HM_HIDDEN, 0.f);
+  for (int l = 0; l < 8; ++l) memcpy(bias.data() + l * HM_HIDDEN, ctx->h_b[l].data(), sizeof(float) * ctx->h_b[l].size());
+  HM_CUDA(cudaMemcpy(ctx->d_tc_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice));
+  return HM_OK;
+}
+
+void hm_tc_free(hm_context* ctx) {
+  if (ctx->d_tc_blob) cudaFree(ctx->d_tc_blob);
+  if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
+  if (ctx->d_tc_masks) cudaFree(ctx->d_tc_masks);
+  if (ctx->d_tc_flags) cudaFree(ctx->d_tc_flags);
+  ctx->d_tc_blob = nullptr;
+  ctx->d_tc_bias = nullptr;
+  ctx->d_tc_masks = nullptr;
+  ctx->d_tc_flags = nullptr;
+}
+
+int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st) {
+  HM_CHECK(ctx->d_tc_blob, "tensor-core engine not initialised");
+  TcParams P;
+  P.plan = ctx->tc_plan;
+  P.blob = ctx->d_tc_blob;
+  P.bias = ctx->d_tc_bias;
+  P.w8 = ctx->d_W[8];
+  P.b8 = ctx->d_b[8];
+  P.rows = rows.d_rows;
+  P.xyz = rows.d_xyz;
+  P.latents = rows.d_latents;
+  P.row_latent = rows.d_row_latent;
+  P.n_dynamic = rows.d_n_dynamic;
+  P.n = rows.n;
+  P.sdf = d_sdf;
+  P.jac = d_jac;
+  P.masks = reinterpret_cast<uint32_t*>(ctx->d_tc_masks);
+  P.flags = ctx->d_tc_flags;
+  P.b0_in_scale_dummy = 0.f;
+  const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
+  const int grid = (int)std::min<int64_t>(n_tiles, ctx->sm_count);
+  if (d_jac)
+    tc_decoder_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(P);
+  else
+    tc_decoder_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(P);
+  ctx->counters.kernel_launches += 1;
+  HM_CUDA(cudaGetLastError());
+  return HM_OK;
+}
+
+// Debug export (not part of the public header): A [64][64] and B [128][64] fp16 bit patterns (host),
+// out [128][256] fp32 (host) = raw TMEM dump after D = A * B^T was issued at (lane_off, col_off).
+extern "C" int hm_debug_tc_selftest(hm_context* ctx, const uint16_t* h_A, const uint16_t* h_B, float* h_out,
+                                    int lane_off, int col_off) {
+  HM_CHECK(ctx && h_A && h_B && h_out, "hm_debug_tc_selftest: null argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  __half *dA = nullptr, *dB = nullptr;
+  float* dO = nullptr;
+  HM_CUDA(cudaMalloc(&dA, 64 * 64 * 2));
+  HM_CUDA(cudaMalloc(&dB, 128 * 64 * 2));
+  HM_CUDA(cudaMalloc(&dO, 128 * 256 * 4));
+  HM_CUDA(cudaMemcpy(dA, h_A, 64 * 64 * 2, cudaMemcpyHostToDevice));
+  HM_CUDA(cudaMemcpy(dB, h_B, 128 * 64 * 2, cudaMemcpyHostToDevice));
+  HM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+  tc_selftest_kernel<<<1, 128, 32768>>>(dA, dB, dO, lane_off, col_off);
+  HM_CUDA(cudaGetLastError());
+  HM_CUDA(cudaDeviceSynchronize());
+  HM_CUDA(cudaMemcpy(h_out, dO, 128 * 256 * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return HM_OK;
+}

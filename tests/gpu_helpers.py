@@ -1,0 +1,37 @@
+"""Helpers for the -m gpu tests: build the product decoder from the golden weights."""
+import numpy as np
+import torch
+
+from tests.helpers import pepper_weights, random_decoder_weights
+
+_cache = {}
+
+
+def pepper_decoder():
+    if "pepper" not in _cache:
+        from hortimapping_b200.decoder import Decoder
+        W, b, codes = pepper_weights()
+        dec = Decoder(W, b)
+        g = np.random.default_rng(0)
+        z = codes[g.integers(0, codes.shape[0], 8192)]
+        x = ((g.random((8192, 3)) * 2 - 1) * 0.15).astype(np.float32)
+        dec.calibrate(torch.from_numpy(np.concatenate([z, x], 1)))
+        _cache["pepper"] = dec
+    return _cache["pepper"]
+
+
+def random_decoder(seed=0):
+    key = ("rand", seed)
+    if key not in _cache:
+        from hortimapping_b200.decoder import Decoder
+        W, b = random_decoder_weights(seed)
+        dec = Decoder(W, b)
+        _cache[key] = (dec, W, b)
+    return _cache[key]
+
+
+def random_rows(n, seed=0, lat_std=0.1, box=0.1):
+    g = np.random.default_rng(seed)
+    z = g.normal(0, lat_std, (n, 32))
+    x = (g.random((n, 3)) * 2 - 1) * box
+    return np.concatenate([z, x], 1).astype(np.float32)
