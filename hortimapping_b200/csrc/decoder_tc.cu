@@ -11,15 +11,17 @@
 //   * activations never leave the SM: the epilogue warps read the accumulator from TMEM, apply
 //     bias/ReLU (or the ReLU mask in the backward pass), re-split to fp16 hi/lo and write the next
 //     layer's A operand straight into shared memory in the 128-byte-swizzled K-major UMMA layout.
-//     The next layer's MMAs start per 128-column slice as soon as that slice of A is written, into
-//     the other half of TMEM (two 256-column accumulators; the 64x512 tile is folded onto the 128
-//     TMEM lanes as 2 x (64 rows x 256 columns)).
+//     The next layer's MMAs start per 128-column slice as soon as that slice of A is written.
+//   * the tensor core accumulates fp32 with round-toward-zero (measured: -9e-6 relative after the 96
+//     chained MMAs of one layer), so each 64-wide k-chunk is accumulated into a fresh TMEM buffer
+//     (two 256-column buffers ping-pong; the 64x512 tile is folded onto the 128 TMEM lanes as
+//     2 x (64 rows x 256 columns)) and the chunk partials are summed in registers in fp32 RN.
 //   * weights (pre-split, pre-scaled, pre-swizzled on the host into 32 KB stage blobs in the exact
 //     order the MMA warp consumes them) stream L2 -> shared memory with cp.async.bulk + mbarrier
 //     complete_tx through a 3-stage ring.
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (+ TMEM alloc),
-// warps 2..5 = epilogue (one per TMEM sub-partition).
+// Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (+ TMEM alloc),
+// warps 2..9 = epilogue (two per TMEM sub-partition, 128 output columns per thread).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -36,12 +38,13 @@ constexpr int kSmemAHi = 0;
 constexpr int kSmemALo = 65536;
 constexpr int kSmemStages = 131072;
 constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;   // 229376
-constexpr int kSmemTotal = kSmemBars + 256;
-constexpr int kThreads = 192;
+constexpr int kSmemTotal = kSmemBars + 256 + 512;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kMaskWordsPerOp = 64 * 16;           // 64 rows x 512 bits
 
 // barrier slots (8 bytes each) inside the barrier block
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_ACC_FULL = 10, BAR_COUNT = 12 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_PART_FULL = 10, BAR_PART_EMPTY = 12, BAR_COUNT = 14 };
 
 struct TcParams {
   hm_tc_plan plan;
@@ -178,9 +181,11 @@ __device__ __forceinline__ void store_a32(uint8_t* smem, int chunk, int row, int
   }
 }
 
-// k-chunk consumption order of an 8-chunk op: pairs (p, p+4) become ready together (the two column
-// halves of the epilogue), so the MMA warp walks 0,4,1,5,2,6,3,7.
-__host__ __device__ __forceinline__ int chunk_of(int pair, int which) { return pair + 4 * which; }
+// k-chunk consumption order of an 8-chunk op.  An epilogue warp (sub-partition sp, column quarter qsel) owns
+// output columns [256*h + 128*qsel, +128) for its two lane halves h; it finishes the 64-column chunks
+// (2*qsel + j) and (4 + 2*qsel + j) together at step j, so the A operand becomes ready in "pairs"
+// P = 2*j + qsel = {0,4}, {2,6}, {1,5}, {3,7}, and that is the order the MMA warp (and the weight blob) walk K.
+__host__ __device__ __forceinline__ int chunk_of(int pair, int which) { return 2 * (pair & 1) + (pair >> 1) + 4 * which; }
 
 template <bool kJac>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
@@ -190,12 +195,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 rows][2 quarters]
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
     for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), 4);
-    for (int b = 0; b < 2; ++b) mbar_init(bar(BAR_ACC_FULL + b), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
@@ -228,21 +234,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The tensor core accumulates fp32 with round-toward-zero (measured on B200: ~ -1e-7 relative per chained
+    // MMA, -9e-6 after the 96 MMAs of one K = 512 layer).  To keep fp32 parity every 64-wide k-chunk gets a
+    // FRESH accumulator (12 MMAs: the two small cross terms first, then hi*hi) in one of two 256-column TMEM
+    // buffers, and the epilogue warps add the chunk partials in registers (fp32 round-to-nearest).
     if (lane == 0) {
-      uint32_t slot = 0, phase = 0, op_seq = 0;
+      uint32_t slot = 0, phase = 0, op_seq = 0, gseq = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int op = 0; op < kOps; ++op, ++op_seq) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t buf = op_seq & 1;
           const uint32_t idesc = make_idesc(HM_TC_TILE_M, o.stage_rows);
           const uint32_t lo_off = (uint32_t)o.stage_rows * 128u;     // lo tile follows the hi tile inside a stage
-          bool first_k = true;
           for (int pair = 0; pair < 4; ++pair) {
             mbar_wait(bar(BAR_A_READY + pair), op_seq & 1);
             tc_fence_after();
             const int nwhich = (o.n_kchunks == 1) ? (pair == 0 ? 1 : 0) : 2;
-            for (int which = 0; which < nwhich; ++which) {
-              const int chunk = chunk_of(pair, which);
+            for (int which = 0; which < nwhich; ++which, ++gseq) {
+              const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(pair, which);
+              const uint32_t buf = gseq & 1;
+              mbar_wait(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1);
+              tc_fence_after();
               const uint32_t a_hi = smem_base + kSmemAHi + chunk * kAChunkBytes;
               const uint32_t a_lo = smem_base + kSmemALo + chunk * kAChunkBytes;
               for (int nb = 0; nb < o.n_nblocks; ++nb) {
@@ -252,32 +263,37 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 const uint32_t w_lo = w_hi + lo_off;
                 const uint32_t d = tmem_base + ((uint32_t)(16 * (nb >> 1)) << 16) + buf * 256 + (nb & 1) * 128;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
-                  const uint64_t dwh = make_desc(w_hi + ks * 32), dwl = make_desc(w_lo + ks * 32);
-                  umma_f16(d, dah, dwh, idesc, (first_k && ks == 0) ? 0u : 1u);
-                  umma_f16(d, dal, dwh, idesc, 1u);
-                  umma_f16(d, dah, dwl, idesc, 1u);
-                }
+                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_lo + ks * 32), make_desc(w_hi + ks * 32), idesc, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(w_lo + ks * 32), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(w_hi + ks * 32), idesc, 1u);
                 umma_commit(bar(BAR_W_EMPTY + slot));
                 if (++slot == kStages) { slot = 0; phase ^= 1; }
               }
-              first_k = false;
+              umma_commit(bar(BAR_PART_FULL + buf));
             }
           }
-          umma_commit(bar(BAR_ACC_FULL + buf));
         }
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (8) =====================
+    const int e = warp - 2;
     const int sp = warp & 3;                 // TMEM sub-partition this warp may read
-    const int half = lane >> 4;              // which 256-column half of the 512-wide tile this thread owns
+    const int qsel = e >> 2;                 // which 128-column quarter pair of the tile this warp owns
+    const int half = lane >> 4;              // lanes 16..31 of a sub-partition hold output columns 256..511
     const int row = 16 * sp + (lane & 15);   // tile row (M = 64 layout: row r <-> lane 32*(r/16) + r%16)
-    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
-    uint32_t* my_masks = P.masks + (size_t)blockIdx.x * 8 * kMaskWordsPerOp + row * 16 + half * 8;
-    uint32_t op_seq = 0;
+    const int col0 = 256 * half + 128 * qsel;   // first global output column of this thread
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * qsel;
+    uint32_t* my_masks = P.masks + (size_t)blockIdx.x * 8 * kMaskWordsPerOp + row * 16 + (col0 >> 5);
+    uint32_t op_seq = 0, gseq = 0;
     int sat = 0;
+    auto publish = [&](int j) {              // this warp's chunks (2*qsel + j) and (4 + 2*qsel + j) are written
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_A_READY + 2 * j + qsel));
+    };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t grow = tile * HM_TC_TILE_M + row;
       const bool row_ok = grow < n_rows;
@@ -287,166 +303,158 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       const float* xyz_src;
       if (P.rows) { lat_src = P.rows + lrow * HM_IN; xyz_src = lat_src + HM_LATENT; }
       else { lat_src = P.latents + (size_t)(P.row_latent ? P.row_latent[lrow] : 0) * HM_LATENT; xyz_src = P.xyz + lrow * 3; }
-      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64)
+      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64), written by the qsel = 0 warps
       {
-        const float s0 = P.plan.ops[0].in_scale;
-        float x[32];
-        if (half == 0) {
+        if (qsel == 0) {
+          const float s0 = P.plan.ops[0].in_scale;
+          float x[32];
+          if (half == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = lat_src[i] * s0;
-        } else {
+            for (int i = 0; i < 32; ++i) x[i] = lat_src[i] * s0;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = (i < 3) ? xyz_src[i] * s0 : 0.f;
+            for (int i = 0; i < 32; ++i) x[i] = (i < 3) ? xyz_src[i] * s0 : 0.f;
+          }
+          store_a32(smem, 0, row, 32 * half, x, sat);
         }
-        store_a32(smem, 0, row, 32 * half, x, sat);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) for (int p = 0; p < 4; ++p) mbar_arrive(bar(BAR_A_READY + p));
+        publish(0);
+        publish(1);
       }
-      float skip[3 + 32];                      // d sdf / d x0 through the skip connection (half 1 threads)
       float f_sdf = 0.f;
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op, ++op_seq) {
-        const uint32_t buf = op_seq & 1;
         const hm_tc_op& o = P.plan.ops[op];
         const float unscale = o.out_unscale;
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
-        mbar_wait(bar(BAR_ACC_FULL + buf), (op_seq >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_acc = t_lane + buf * 256;
+        // ---- sum the per-chunk partial accumulators in registers (round-to-nearest)
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+        const int ngroups = o.n_kchunks;
+        const int nq = (o.stage_rows == 64) ? ((qsel == 0) ? 2 : 0) : 4;      // B0: 64 output columns, all in quarter 0
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g, ++gseq) {
+          const uint32_t buf = gseq & 1;
+          mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nq) {
+              float v[32];
+              tmem_ld32(t_lane + buf * 256 + q * 32, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_PART_EMPTY + buf));
+        }
         if (op < 7) {
           // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next
-          const float* bias = P.bias + op * HM_HIDDEN + 256 * half;
+          const float* bias = P.bias + op * HM_HIDDEN + col0;
           const float k_mul = unscale * s_next;
           uint32_t* mrow = my_masks + op * kMaskWordsPerOp;
-#pragma unroll 1
-          for (int p = 0; p < 4; ++p) {
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-              const int lc = p * 64 + j * 32;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int lc = j * 64 + u * 32;
               float v[32];
-              tmem_ld32(t_acc + lc, v);
               uint32_t m = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float y = fmaf(v[i], k_mul, __ldg(bias + lc + i) * s_next);
+                float y = fmaf(acc[lc + i], k_mul, __ldg(bias + lc + i) * s_next);
                 m |= (y > 0.f ? 1u : 0u) << i;
                 v[i] = fmaxf(y, 0.f);
               }
-              if (op == 3) {
+              if (op == 3 && col0 + lc + 32 > HM_SKIP_COL) {
                 // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
-                const int gc0 = 256 * half + lc;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const int gc = gc0 + i;
-                  if (gc >= HM_SKIP_COL) {
-                    const int k = gc - HM_SKIP_COL;
+                  const int k = col0 + lc + i - HM_SKIP_COL;
+                  if (k >= 0) {
                     v[i] = (k < HM_LATENT ? lat_src[k] : xyz_src[k - HM_LATENT]) * s_next;
                     m &= ~(1u << i);
                   }
                 }
               }
-              if (kJac) mrow[p * 2 + j] = m;
-              store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+              if (kJac) mrow[j * 2 + u] = m;
+              store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+            publish(j);
           }
         } else if (op == 7) {
           // ---------------- lin7 epilogue + lin8 + tanh (deep_sdf_decoder.py:107-108)
-          const float* bias = P.bias + 7 * HM_HIDDEN + 256 * half;
-          const float* w8 = P.w8 + 256 * half;
-          uint32_t mk[8];
+          const float* bias = P.bias + 7 * HM_HIDDEN + col0;
+          const float* w8 = P.w8 + col0;
+          uint32_t mk[4];
           float dot = 0.f;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float v[32];
-            tmem_ld32(t_acc + q * 32, v);
+          for (int q = 0; q < 4; ++q) {
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float y = fmaf(v[i], unscale, __ldg(bias + q * 32 + i));
+              float y = fmaf(acc[q * 32 + i], unscale, __ldg(bias + q * 32 + i));
               m |= (y > 0.f ? 1u : 0u) << i;
               dot = fmaf(fmaxf(y, 0.f), __ldg(w8 + q * 32 + i), dot);
             }
             mk[q] = m;
           }
           dot += __shfl_xor_sync(0xffffffffu, dot, 16);
-          f_sdf = tanhf(dot + __ldg(P.b8));
-          if (half == 0 && row_ok) P.sdf[grow] = f_sdf;
+          if (half == 0) dot_scratch[row * 2 + qsel] = dot;
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          f_sdf = tanhf(dot_scratch[row * 2] + dot_scratch[row * 2 + 1] + __ldg(P.b8));
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (half == 0 && qsel == 0 && row_ok) P.sdf[grow] = f_sdf;
           if (kJac) {
             // d7 = (1 - f^2) * w8 * relu'(h7): A operand of B7
             const float coef = (1.f - f_sdf * f_sdf) * s_next;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int j = 0; j < 2; ++j) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int q = p * 2 + j;
+              for (int u = 0; u < 2; ++u) {
+                const int q = j * 2 + u;
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = ((mk[q] >> i) & 1u) ? coef * __ldg(w8 + q * 32 + i) : 0.f;
-                store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+                store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
               }
-              fence_proxy_async();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+              publish(j);
             }
-          } else {
-            tc_fence_before();
           }
         } else if (op < 15) {
           // ---------------- backward through lin_l (l = 15 - op = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
           const int l = 15 - op;
           const uint32_t* mrow = my_masks + (l - 1) * kMaskWordsPerOp;
           const float k_mul = unscale * s_next;
-#pragma unroll 1
-          for (int p = 0; p < 4; ++p) {
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-              const int lc = p * 64 + j * 32;
-              const uint32_t m = mrow[p * 2 + j];
+          if (l == 4 && col0 == 384 && row_ok) {
+            // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
+            // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
+            float* jrow = P.jac + grow * HM_IN;
+#pragma unroll
+            for (int k = 0; k < HM_IN; ++k) __stcg(jrow + k, acc[HM_SKIP_COL - 384 + k] * unscale);
+            __threadfence_block();
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int lc = j * 64 + u * 32;
+              const uint32_t m = mrow[j * 2 + u];
               float v[32];
-              tmem_ld32(t_acc + lc, v);
-              if (l == 4 && p == 3) {
-                // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0.
-                // They live in the half-1 lanes: local columns 221..255 = (j=0: i=29..31), (j=1: i=0..31).
-                // (half-0 lanes fill their own copy with values nobody reads.)
-                if (j == 0) {
-                  skip[0] = v[29] * unscale; skip[1] = v[30] * unscale; skip[2] = v[31] * unscale;
-                } else {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) skip[3 + i] = v[i] * unscale;
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] * k_mul : 0.f;
-              store_a32(smem, 4 * half + p, row, j * 32, v, sat);
+              for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? acc[lc + i] * k_mul : 0.f;
+              store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_A_READY + p));
+            publish(j);
           }
         } else {
-          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all in the half-0 lanes) + skip gradient
-          float v0[32], v1[32];
-          tmem_ld32(t_acc, v0);
-          tmem_ld32(t_acc + 32, v1);
-          tc_fence_before();
-          float* jrow = P.jac + grow * HM_IN;
+          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all in the half-0 lanes of quarter 0) + skip gradient
+          if (qsel == 0 && half == 0 && row_ok) {
+            float* jrow = P.jac + grow * HM_IN;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float sk = __shfl_down_sync(0xffffffffu, skip[i], 16);
-            if (half == 0 && row_ok) jrow[i] = fmaf(v0[i], unscale, sk);
-          }
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            float sk = __shfl_down_sync(0xffffffffu, skip[32 + i], 16);
-            if (half == 0 && row_ok) jrow[32 + i] = fmaf(v1[i], unscale, sk);
+            for (int k = 0; k < HM_IN; ++k) jrow[k] = fmaf(acc[k], unscale, __ldcg(jrow + k));
           }
         }
       }
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 // accumulator layout with an optional +16 lane offset, 32x32b TMEM loads); dumps all 128 lanes x 256
 // columns so the host can check the layout assumptions.
 __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
-                                                             float* __restrict__ out, int lane_off, int col_off) {
+                                                             float* __restrict__ out, int lane_off, int col_off, int repeats) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t done_bar;
@@ -494,7 +502,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __res
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc(64, 128);
     const uint32_t d = tb + ((uint32_t)lane_off << 16) + col_off;
-    for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, ks ? 1u : 0u);
+    for (int rep = 0; rep < repeats; ++rep)
+      for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep | ks) ? 1u : 0u);
     umma_commit(smem_u32(&done_bar));
   }
   mbar_wait(smem_u32(&done_bar), 0);
@@ -560,7 +569,7 @@ int hm_tc_init(hm_context* ctx) {
     const int npairs = (o.n_kchunks == 1) ? 1 : 4;
     for (int pair = 0; pair < npairs; ++pair)
       for (int which = 0; which < ((o.n_kchunks == 1) ? 1 : 2); ++which) {
-        const int chunk = chunk_of(pair, which);
+        const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(pair, which);
         for (int nb = 0; nb < o.n_nblocks; ++nb) {
           size_t at = blob.size();
           blob.resize(at + stage_bytes, 0);
@@ -639,7 +648,7 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
 // Debug export (not part of the public header): A [64][64] and B [128][64] fp16 bit patterns (host),
 // out [128][256] fp32 (host) = raw TMEM dump after D = A * B^T was issued at (lane_off, col_off).
 extern "C" int hm_debug_tc_selftest(hm_context* ctx, const uint16_t* h_A, const uint16_t* h_B, float* h_out,
-                                    int lane_off, int col_off) {
+                                    int lane_off, int col_off, int repeats) {
   HM_CHECK(ctx && h_A && h_B && h_out, "hm_debug_tc_selftest: null argument");
   HM_CUDA(cudaSetDevice(ctx->device));
   __half *dA = nullptr, *dB = nullptr;
@@ -650,7 +659,7 @@ extern "C" int hm_debug_tc_selftest(hm_context* ctx, const uint16_t* h_A, const 
   HM_CUDA(cudaMemcpy(dA, h_A, 64 * 64 * 2, cudaMemcpyHostToDevice));
   HM_CUDA(cudaMemcpy(dB, h_B, 128 * 64 * 2, cudaMemcpyHostToDevice));
   HM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
-  tc_selftest_kernel<<<1, 128, 32768>>>(dA, dB, dO, lane_off, col_off);
+  tc_selftest_kernel<<<1, 128, 32768>>>(dA, dB, dO, lane_off, col_off, repeats < 1 ? 1 : repeats);
   HM_CUDA(cudaGetLastError());
   HM_CUDA(cudaDeviceSynchronize());
   HM_CUDA(cudaMemcpy(h_out, dO, 128 * 256 * 4, cudaMemcpyDeviceToHost));

@@ -38,7 +38,7 @@ class _SdfRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, dec: "Decoder", rows: torch.Tensor):
-        need = rows.requires_grad and torch.is_grad_enabled()
+        need = bool(ctx.needs_input_grad[1])
         sdf, jac = dec._eval_rows(rows, with_jac=need)
         if need:
             ctx.save_for_backward(jac)
@@ -47,7 +47,7 @@ class _SdfRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (jac,) = ctx.saved_tensors
-        return None, grad_out.reshape(-1, 1) * jac
+        return None, (grad_out.reshape(-1, 1) * jac.reshape(-1, HM_IN)).reshape(jac.shape)
 
 
 class Decoder:

@@ -19,6 +19,24 @@ SDF_TOL = dict(rtol=1e-4, atol=1e-6)
 JAC_TOL = dict(rtol=1e-4, atol=2e-6)
 
 
+def assert_jac_close(actual, ref, rtol=1e-4, atol=2e-6, max_bad_rows=3e-3, what=""):
+    """Row-wise Jacobian comparison.  d sdf / d input of a ReLU network is piecewise constant in the
+    activation pattern: a hidden unit whose pre-activation is within fp32 rounding of zero (measured: the
+    closest of 4096 units x 1000 rows sits at 8e-8 of its operand scale) switches sides between two
+    correct fp32 evaluations and changes that row's whole gradient by O(10 %).  The reference has the same
+    property between its CPU and CUDA runs.  So: all rows but a vanishing fraction must agree to the stated
+    tolerance; the rest are reported."""
+    actual = np.asarray(actual).reshape(-1, 35)
+    ref = np.asarray(ref).reshape(-1, 35)
+    bad = (np.abs(actual - ref) > rtol * np.abs(ref) + atol).any(1)
+    allowed = max(1, int(np.ceil(max_bad_rows * len(bad))))
+    assert bad.sum() <= allowed, f"{what}: {bad.sum()} of {len(bad)} rows off (allowed {allowed}); max abs err " \
+                                 f"{np.abs(actual - ref).max():.3e}"
+    good = ~bad
+    if good.any():
+        np.testing.assert_allclose(actual[good], ref[good], rtol=rtol, atol=atol)
+
+
 def test_tcgen05_selftest_layouts():
     """One 64x128x64 fp16 GEMM through the kernel's descriptor / TMEM-layout building blocks."""
     from hortimapping_b200 import _lib
@@ -29,11 +47,11 @@ def test_tcgen05_selftest_layouts():
     B = g.integers(-4, 5, (128, 64)).astype(np.float16)
     ref = A.astype(np.float32) @ B.astype(np.float32).T          # exact in fp32
     L = _lib.lib()
-    L.hm_debug_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.hm_debug_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     for lane_off, col_off in ((0, 0), (16, 0), (0, 128), (16, 128)):
         out = np.zeros((128, 256), np.float32)
         _lib.check(L.hm_debug_tc_selftest(dec.handle, A.view(np.uint16).ctypes.data, B.view(np.uint16).ctypes.data,
-                                          out.ctypes.data, lane_off, col_off), "selftest")
+                                          out.ctypes.data, lane_off, col_off, 1), "selftest")
         # M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16 (+ lane_off)
         lanes = np.array([32 * (r // 16) + r % 16 + lane_off for r in range(64)])
         got = out[lanes, col_off:col_off + 128]
@@ -61,18 +79,18 @@ def test_decoder_rows_vs_reference_golden(engine):
         inp = rows.unsqueeze(1).clone().requires_grad_(True)
         y = dec(inp)
         (gr,) = torch.autograd.grad(y, inp, torch.ones_like(y))
-        np.testing.assert_allclose(gr.cpu().numpy(), g["jac"], **JAC_TOL)
+        assert_jac_close(gr.cpu().numpy(), g["jac"], what="autograd")
         # fp64 reference: the device result must be as close to the truth as the fp32 reference is (x4 slack)
         e_dev = np.abs(y.detach().cpu().numpy().reshape(-1) - g["sdf64"].reshape(-1)).max()
         e_ref = np.abs(g["sdf3d"].reshape(-1) - g["sdf64"].reshape(-1)).max()
-        assert e_dev < 4 * e_ref + 1e-7, (e_dev, e_ref)
+        assert e_dev < 4 * e_ref + 5e-8, (e_dev, e_ref)
         lat, xyz = torch.from_numpy(g["lat"]).cuda(), torch.from_numpy(g["xyz"]).cuda()
         from hortimapping_b200.decoder import decode_sdf, get_batch_sdf_jacobian
         np.testing.assert_allclose(decode_sdf(dec, lat, xyz).cpu().numpy(), g["decode_sdf"], **SDF_TOL)
         yb, gb = get_batch_sdf_jacobian(dec, lat, xyz)
         assert tuple(yb.shape) == g["batch_y"].shape and tuple(gb.shape) == g["batch_g"].shape
         np.testing.assert_allclose(yb.cpu().numpy(), g["batch_y"], **SDF_TOL)
-        np.testing.assert_allclose(gb.cpu().numpy(), g["batch_g"], **JAC_TOL)
+        assert_jac_close(gb.cpu().numpy(), g["batch_g"], what="batch")
     finally:
         dec.set_engine("tc")
 
@@ -96,7 +114,10 @@ def test_alive_random_decoder_vs_oracle(engine):
         (gr,) = torch.autograd.grad(y, t, torch.ones_like(y))
         scale = np.abs(j_ref).max()
         np.testing.assert_allclose(y.detach().cpu().numpy(), y_ref, rtol=1e-4, atol=2e-6)
-        np.testing.assert_allclose(gr.cpu().numpy(), j_ref, rtol=1e-4, atol=2e-6 * max(scale, 1.0))
+        # numpy fp32 vs fp64 of the SAME oracle already flips 3 of these 4096 rows (all 4096 hidden units alive,
+        # larger weights than the shipped model); the engines' operand rounding (2^-22 for the fp16 split)
+        # is ~4x fp32's 2^-24, hence ~4x the flips.
+        assert_jac_close(gr.cpu().numpy(), j_ref, rtol=1e-4, atol=2e-6 * max(scale, 1.0), max_bad_rows=1e-2, what="alive")
     finally:
         dec.set_engine("tc")
 
@@ -114,7 +135,7 @@ def test_ragged_row_counts(n):
         np.testing.assert_allclose(y.cpu().numpy(), ref, **SDF_TOL)
         _, gr = dec._eval_rows(t, with_jac=True)
         _, jref = oracle_decoder().forward_jac(rows)
-        np.testing.assert_allclose(gr.cpu().numpy(), jref, **JAC_TOL)
+        assert_jac_close(gr.cpu().numpy(), jref, what=f"n={n}")
 
 
 def test_voxel_grid_bit_exact_and_grid_sdf():
@@ -148,7 +169,7 @@ def test_tc_and_simt_engines_agree_on_a_large_batch():
     finally:
         dec.set_engine("tc")
     np.testing.assert_allclose(y_tc.cpu().numpy(), y_s.cpu().numpy(), **SDF_TOL)
-    np.testing.assert_allclose(j_tc.cpu().numpy(), j_s.cpu().numpy(), **JAC_TOL)
+    assert_jac_close(j_tc.cpu().numpy(), j_s.cpu().numpy(), what="tc vs simt")
     perm = torch.randperm(n, device="cuda")
     y_p, _ = dec._eval_rows(t[perm], with_jac=False)
     assert torch.equal(y_p, y_tc[perm]), "a row's SDF must not depend on its tile neighbours"
