@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- fruits/sec of the shape-completion inner loop on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): 64 synthetic fruit instances x 2048 observed surface points x
+200 LM iterations per GPU, decoder-only path = `Optimizer.shape_opt_deepsdf`
+(wild_completion/optimizer.py:306-429) batched over the fruits, all epsilon_* = 0 so no fruit exits
+early ("200 Adam iters" in BASELINE.json is the reference's LM loop).
+
+A step = one batched optimise call (64 fruits x 200 iterations).  `value` times K steps with the inputs
+resident in HBM; `e2e` times the same K steps through the C-ABI host-buffer entry point
+(hm_optimize_shape_host: pinned host inputs -> H2D -> loop -> D2H of latents/poses/iter counts).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1 runs under torchrun (one rank per GPU, fruits sharded, one NCCL all-gather of the 49-float result
+records per step).  `--impl reference` times the CPU oracle port (the reference's algorithm restated in
+numpy, oracle/hm_oracle.py) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_FRUITS, N_PTS, N_ITERS = 64, 2048, 200
+FLOP_PER_JAC_ROW = 7_342_080           # 2 x 1 835 520 MAC forward + the same backward
+METRIC = "fruits/sec (200 iters, 2048 pts)"
+
+WILD_CFG = {
+    "device": "cuda",
+    "opt": {"scale_on": True,
+            "lm": {"lm_on": True, "lm_eye": False, "lm_lambda_0": 0.1, "s_damp": 1e-3},
+            "recon": {"n_pts": 2000, "cluster_dist_m": 0.01, "robust_th_m": 0.01},
+            "render": {"n_fg_pix": 200, "n_bg_pix": 200, "n_bg_pad": 20, "n_frame": 10, "n_sample_on_ray": 30,
+                       "log_sdf_occ": True, "occ_cutoff_m": 0.01, "occlusion_on": True, "robust_th_m": 0.05},
+            "weight": {"w_recon": 1, "w_depth": 5e-2, "w_mask": 5e-4, "w_codereg": 5e-4},
+            "converge": {"max_iter": N_ITERS, "epsilon_g": 0, "epsilon_c": 0, "epsilon_t": 0, "epsilon_r": 0, "epsilon_s": 0},
+            "robust_iter": 5},
+    "vis": {"log_on": False, "vis_on": False, "vis_pause_s": 0.0, "object_radius_max_m": 0.08, "mc_res_mm": 4.0},
+}   # configs/wild_pepper.yaml of the reference with max_iter 200, epsilons 0, vis off
+
+
+def load_weights():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sweetpepper_32.npz"))
+    return [z[f"W{l}"] for l in range(9)], [z[f"b{l}"] for l in range(9)], z["latent_codes"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(dec, codes, seed: int, rank: int):
+    """Synthetic fruits of the SURVEY 8d generator (points only), built with the product decoder."""
+    import torch
+    from hortimapping_b200 import synth
+
+    def sdf_jac(latent, pts):
+        y, g = dec.sdf_jacobian(torch.from_numpy(np.asarray(latent, np.float32)), torch.from_numpy(np.asarray(pts, np.float32)))
+        return y.reshape(-1).cpu().numpy(), g.reshape(-1, 35)[:, 32:].cpu().numpy()
+
+    pts, T_ow = [], []
+    if os.environ.get("HM_BENCH_RANDOM_POINTS"):       # profiling aid: skip the surface projection launches
+        g = np.random.default_rng(seed + rank)
+        p = ((g.random((N_FRUITS, N_PTS, 3)) * 2 - 1) * 0.045).astype(np.float32)
+        return p, np.tile(np.eye(4, dtype=np.float32), (N_FRUITS, 1, 1)), np.tile(codes.mean(0).astype(np.float32), (N_FRUITS, 1))
+    for i in range(N_FRUITS):
+        fr = synth.make_fruit(sdf_jac, codes, seed, rank * N_FRUITS + i, n_pts=N_PTS, with_rays=False)
+        pts.append(fr.points_w)
+        T_ow.append(np.linalg.inv(fr.T_wo_gt.astype(np.float64)).astype(np.float32))   # pose known for the DeepSDF baseline
+    init_lat = np.tile(codes.mean(0).astype(np.float32), (N_FRUITS, 1))
+    return np.stack(pts), np.stack(T_ow), init_lat
+
+
+def cpu_baseline_sample(n_iters: int, points_w, T_ow, init_lat):
+    """The oracle port on the host cores: ONE fruit x 2048 points x n_iters LM iterations, scaled to 200."""
+    from oracle import hm_oracle as O
+    W, b, _ = load_weights()
+    dec = O.DecoderOracle(W, b, (4,), np.float32)
+    cfg = copy.deepcopy(WILD_CFG)
+    cfg["opt"]["converge"]["max_iter"] = n_iters
+    lat = init_lat.copy()
+    t0 = time.perf_counter()
+    O.shape_opt_deepsdf(dec, cfg, lat, T_ow, points_w)
+    dt = time.perf_counter() - t0
+    return 1.0 / (dt * N_ITERS / n_iters), dt
+
+
+def synth_points_cpu(seed=0):
+    """Inputs for the CPU arm without touching the GPU: random points near the mean shape's surface are not
+    needed for timing -- any 2048 points in the object cube cost the same FLOPs."""
+    g = np.random.default_rng(seed)
+    pts = ((g.random((N_PTS, 3)) * 2 - 1) * 0.045).astype(np.float32)
+    return pts, np.eye(4, dtype=np.float32)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, b, codes = load_weights()
+    pts, T = synth_points_cpu()
+    init = codes.mean(0).astype(np.float32)
+    n_it = 20
+    try:
+        import torch
+        threads = torch.get_num_threads()
+    except Exception:
+        threads = os.cpu_count()
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(4, pts, T, init)
+    times = []
+    for _ in range(args.steps):
+        v, dt = cpu_baseline_sample(n_it, pts, T, init)
+        times.append(dt)
+    step_s = sum(times) / len(times)
+    value = 1.0 / (step_s * N_ITERS / n_it)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "fruits/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "64 fruits x 2048 pts x 200 LM iters, decoder-only (shape_opt_deepsdf)",
+                      "sample": f"1 fruit x {N_PTS} pts x {n_it} of 200 iterations per step, scaled x{N_ITERS // n_it}"},
+           "cpu_baseline": {"value": value, "unit": "fruits/s", "cores": os.cpu_count(), "threads": threads, "kind": "port",
+                            "sample": f"oracle/hm_oracle.py shape_opt_deepsdf, 1 fruit x {N_PTS} pts x {n_it} iterations, scaled to 200"},
+           "e2e": {"value": value, "unit": "fruits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--iters", type=int, default=N_ITERS, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from hortimapping_b200 import _lib
+    from hortimapping_b200.decoder import Decoder
+    from hortimapping_b200.optimizer import Optimizer, opt_params_from_cfg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    W, b, codes = load_weights()
+    dec = Decoder(W, b, device=local)
+    g = np.random.default_rng(0)
+    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 8192)], ((g.random((8192, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
+    dec.calibrate(torch.from_numpy(cal))
+    cfg = copy.deepcopy(WILD_CFG)
+    cfg["opt"]["converge"]["max_iter"] = args.iters
+    opt = Optimizer(cfg, dec, None, None)
+    pts, T_ow, init_lat = make_inputs(dec, codes, seed=7, rank=rank)
+
+    # ---- device-resident arm
+    d_pts = [torch.from_numpy(pts[i]).to(dev) for i in range(N_FRUITS)]
+    lat0 = torch.from_numpy(init_lat).to(dev)
+    T0 = torch.from_numpy(T_ow).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    gathered = torch.empty(world * N_FRUITS, 49, device=dev)
+
+    from hortimapping_b200.optimizer import PackedBatch
+    pk = PackedBatch([p for p in pts], None, 0, np.zeros(N_FRUITS, np.float32), np.zeros(N_FRUITS, bool))
+    params = opt_params_from_cfg(cfg["opt"])
+
+    def step_device():
+        lat, T = lat0.clone(), T0.clone()
+        iters, status = opt._run(pk, lat, T, params)
+        rec = torch.cat([lat, T.reshape(N_FRUITS, 16), iters.float().reshape(-1, 1)], 1)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)
+        else:
+            gathered.copy_(rec)
+        flush.zero_()
+        return lat, iters
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync()
+    c0 = dec.counters()
+    dec.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(args.steps):
+        lat_out, iters_out = step_device()
+    ev1.record()
+    sync()
+    clocks = sampler.stop()
+    dec.profile(False)
+    c1 = dec.counters()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    assert int(iters_out.min().item()) == args.iters, "a fruit exited early: the workload is not fixed"
+    value = world * N_FRUITS * args.steps / (total_ms / 1e3) * (args.iters / N_ITERS)   # --iters != 200 is a debug aid only
+
+    # ---- roofline of the dominant kernel (tc_decoder_kernel<jac>), timed live with CUDA events inside the step
+    n_launch = c1["decoder_launches"] - c0["decoder_launches"]
+    dec_ms = c1["decoder_ms"] - c0["decoder_ms"]
+    rows_per_launch = N_FRUITS * N_PTS
+    flop_per_launch = rows_per_launch * FLOP_PER_JAC_ROW
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        pk_json = json.load(open(peaks_file))
+        peak, peak_src = float(pk_json["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    else:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    achieved = flop_per_launch / (dec_ms / max(n_launch, 1) * 1e-3) / 1e12 if n_launch else None
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tfile):
+        traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "tc_decoder_kernel<true> (fused DeepSDF forward + input gradient)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_flop_per_launch": flop_per_launch,
+                "issued_mma_flop_per_launch": 3 * flop_per_launch, "launches": n_launch, "avg_launch_ms": dec_ms / max(n_launch, 1),
+                "kernel_share_of_step": dec_ms / total_ms}
+
+    # ---- end-to-end arm: C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
+    h_lat = torch.from_numpy(init_lat).pin_memory()
+    h_T = torch.from_numpy(T_ow).pin_memory()
+    h_pts = torch.from_numpy(pts.reshape(-1, 3)).pin_memory()
+    h_it = torch.zeros(N_FRUITS, dtype=torch.int32).pin_memory()
+    h_st = torch.zeros(N_FRUITS, dtype=torch.int32).pin_memory()
+    offsets = (np.arange(N_FRUITS + 1) * N_PTS).astype(np.int64)
+    hb = _lib.FruitBatch()
+    hb.n_fruits = N_FRUITS
+    hb.h_point_offsets = offsets.ctypes.data
+    hb.d_points_w = h_pts.data_ptr()
+    hb.d_iter_count, hb.d_status = h_it.data_ptr(), h_st.data_ptr()
+    h2d = h_lat.numel() * 4 + h_T.numel() * 4 + h_pts.numel() * 4
+    d2h = h_lat.numel() * 4 + h_T.numel() * 4 + h_it.numel() * 4 + h_st.numel() * 4
+
+    def step_host():
+        w_lat, w_T = h_lat.clone().pin_memory(), h_T.clone().pin_memory()
+        hb.d_latents, hb.d_T_ow = w_lat.data_ptr(), w_T.data_ptr()
+        _lib.check(dec._L.hm_optimize_shape_host(dec.handle, C.byref(params), C.byref(hb)), "hm_optimize_shape_host")
+        return w_lat
+
+    step_host()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        w_lat = step_host()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_FRUITS * args.steps / float(e2e_s.item()) * (args.iters / N_ITERS)
+    assert torch.allclose(w_lat.to(dev), lat_out, rtol=0, atol=0), "host and device arms disagree"
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+
+    out = {"metric": METRIC, "value": value, "unit": "fruits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{N_FRUITS} fruits/GPU x {N_PTS} pts x {args.iters} LM iters, decoder-only (shape_opt_deepsdf), "
+                                  "sweetpepper_32 weights, epsilons 0",
+                      "parallelism": f"fruits sharded over {world} GPU(s), one all-gather of 49-float records per step",
+                      "l2": "256 MiB buffer written between steps (L2 flush); weights are L2-resident by design within a step",
+                      "arithmetic": "fp32 semantics: split-fp16 tcgen05 MMAs (3 per product), fp32 accumulate, per-k-chunk promotion"},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": e2e_value, "unit": "fruits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "roofline": roofline}
+    if rank == 0:
+        if world == 1:
+            cv, cdt = cpu_baseline_sample(20, pts[0], T_ow[0], init_lat[0])
+            try:
+                threads = torch.get_num_threads()
+            except Exception:
+                threads = os.cpu_count()
+            out["cpu_baseline"] = {"value": cv, "unit": "fruits/s", "cores": os.cpu_count(), "threads": threads, "kind": "port",
+                                   "sample": f"oracle/hm_oracle.py shape_opt_deepsdf (numpy/OpenBLAS), 1 fruit x {N_PTS} pts x 20 iterations "
+                                             f"({cdt:.1f} s), scaled to 200"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,14 +46,14 @@ class FruitBatch(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("rows_forward", C.c_int64), ("rows_jacobian", C.c_int64), ("kernel_launches", C.c_int64),
-                ("iterations", C.c_int64)]
+                ("iterations", C.c_int64), ("decoder_launches", C.c_int64), ("decoder_ms", C.c_double)]
 
 
 _lib = None
 
 # every symbol include/hortimapping_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_calibrate",
-           "hm_get_counters", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
+           "hm_get_counters", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
            "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host"]
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.hm_get_engine.argtypes = [C.c_void_p]
     L.hm_calibrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hm_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    L.hm_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.hm_sdf_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.hm_sdf_forward_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.hm_sdf_jacobian.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]

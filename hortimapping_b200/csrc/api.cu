@@ -126,7 +126,9 @@ extern "C" void hm_destroy(hm_context* ctx) {
   hm_tc_free(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pinned) cudaFree(ctx->pinned);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->d_last_H) cudaFree(ctx->d_last_H);
   if (ctx->d_last_b) cudaFree(ctx->d_last_b);
   if (ctx->d_last_dx) cudaFree(ctx->d_last_dx);
@@ -142,9 +144,25 @@ extern "C" int hm_set_engine(hm_context* ctx, int engine) {
 
 extern "C" int hm_get_engine(const hm_context* ctx) { return ctx ? ctx->engine : HM_ERR_INVALID; }
 
-extern "C" int hm_get_counters(const hm_context* ctx, hm_counters* out) {
+extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
   HM_CHECK(ctx && out, "hm_get_counters: null argument");
+  for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
+    float ms = 0.f;
+    HM_CUDA(cudaEventSynchronize(ctx->prof_events[i + 1]));
+    HM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    ctx->counters.decoder_ms += ms;
+    ctx->counters.decoder_launches += 1;
+    ctx->prof_pool.push_back(ctx->prof_events[i]);
+    ctx->prof_pool.push_back(ctx->prof_events[i + 1]);
+  }
+  ctx->prof_events.clear();
   *out = ctx->counters;
+  return HM_OK;
+}
+
+extern "C" int hm_profile_enable(hm_context* ctx, int on) {
+  HM_CHECK(ctx, "hm_profile_enable: null context");
+  ctx->profiling = on ? 1 : 0;
   return HM_OK;
 }
 
@@ -167,7 +185,23 @@ int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, 
   if (rows.n <= 0) return HM_OK;
   if (d_jac) ctx->counters.rows_jacobian += rows.n; else ctx->counters.rows_forward += rows.n;
   if (ctx->engine == HM_ENGINE_SIMT) return hm_simt_decode(ctx, rows, d_sdf, d_jac, st, nullptr);
-  return hm_tc_decode(ctx, rows, d_sdf, d_jac, st);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profiling) {
+    auto get = [&](cudaEvent_t& e) -> cudaError_t {
+      if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return cudaSuccess; }
+      return cudaEventCreate(&e);
+    };
+    HM_CUDA(get(e0));
+    HM_CUDA(get(e1));
+    HM_CUDA(cudaEventRecord(e0, st));
+  }
+  int rc = hm_tc_decode(ctx, rows, d_sdf, d_jac, st);
+  if (ctx->profiling) {
+    HM_CUDA(cudaEventRecord(e1, st));
+    ctx->prof_events.push_back(e0);
+    ctx->prof_events.push_back(e1);
+  }
+  return rc;
 }
 
 extern "C" int hm_sdf_forward(hm_context* ctx, const float* d_latent, const float* d_xyz, int64_t n, float* d_sdf, void* stream) {

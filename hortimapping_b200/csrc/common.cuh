@@ -85,6 +85,9 @@ struct hm_context {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   hm_counters counters = {};
+  int profiling = 0;
+  std::vector<cudaEvent_t> prof_events;      // (begin, end) pairs awaiting read-back
+  std::vector<cudaEvent_t> prof_pool;
   // last LM system (test hook)
   float* d_last_H = nullptr;
   float* d_last_b = nullptr;

@@ -116,6 +116,9 @@ class Decoder:
         rows = _f32c(rows.reshape(-1, HM_IN), self.device)
         check(self._L.hm_calibrate(self._h, rows.data_ptr(), rows.shape[0], _stream_ptr(self.device)), "hm_calibrate")
 
+    def profile(self, on: bool):
+        check(self._L.hm_profile_enable(self._h, int(bool(on))), "hm_profile_enable")
+
     def counters(self) -> dict:
         c = _lib.Counters()
         check(self._L.hm_get_counters(self._h, C.byref(c)), "hm_get_counters")

@@ -104,8 +104,10 @@ class Optimizer(object):
     def _run(self, pk: PackedBatch, latents: torch.Tensor, T_ow: torch.Tensor, params: _lib.OptParams):
         dec = self.decoder
         dev = dec.device
-        t = lambda a: torch.from_numpy(a).to(dev)
-        keep = [t(pk.points)]
+        if getattr(pk, "_dev", None) is None:       # inputs are uploaded once per PackedBatch and stay resident
+            t = lambda a: torch.from_numpy(a).to(dev)
+            pk._dev = [t(pk.points)] + ([t(pk.T_wc), t(pk.rays), t(pk.depth_obs)] if pk.joint else [])
+        keep = pk._dev
         b = _lib.FruitBatch()
         b.n_fruits = pk.n_fruits
         b.d_latents, b.d_T_ow = latents.data_ptr(), T_ow.data_ptr()
@@ -115,7 +117,6 @@ class Optimizer(object):
         status = torch.zeros(pk.n_fruits, dtype=torch.int32, device=dev)
         b.d_iter_count, b.d_status = iters.data_ptr(), status.data_ptr()
         if pk.joint:
-            keep += [t(pk.T_wc), t(pk.rays), t(pk.depth_obs)]
             b.h_frame_offsets = pk.frame_offsets.ctypes.data
             b.d_T_wc, b.d_rays, b.d_depth_obs = keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr()
             b.h_ray_offsets, b.h_n_fg = pk.ray_offsets.ctypes.data, pk.n_fg.ctypes.data

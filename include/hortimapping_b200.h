@@ -118,6 +118,8 @@ typedef struct hm_counters {
   int64_t rows_jacobian;      /* decoder rows evaluated forward + input gradient             */
   int64_t kernel_launches;    /* kernels of this library launched                            */
   int64_t iterations;         /* LM iterations launched (max over fruits)                    */
+  int64_t decoder_launches;   /* decoder kernel launches timed while profiling was enabled   */
+  double decoder_ms;          /* sum of their CUDA-event durations (ms)                      */
 } hm_counters;
 
 const char* hm_last_error(void);
@@ -130,7 +132,10 @@ int hm_set_engine(hm_context* ctx, int engine);
 int hm_get_engine(const hm_context* ctx);
 /* Choose the power-of-two fp16 operand scales of the TC engine from sample rows [n][35] (device). */
 int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
-int hm_get_counters(const hm_context* ctx, hm_counters* out);
+/* Counters are cumulative since hm_create.  With profiling enabled every decoder kernel launch is bracketed
+ * by CUDA events on its stream; hm_get_counters then waits for the recorded events and adds their durations. */
+int hm_get_counters(hm_context* ctx, hm_counters* out);
+int hm_profile_enable(hm_context* ctx, int on);
 
 /* wild_completion/utils.py:144-172 decode_sdf: sdf[i] = f(latent, xyz[i]). */
 int hm_sdf_forward(hm_context* ctx, const float* d_latent, const float* d_xyz, int64_t n, float* d_sdf, void* stream);

@@ -1,0 +1,116 @@
+"""CPU tests of the host-side logic of the product package (no GPU, no compute calls into the library)."""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import cfg_of, load_npz, render_data_of
+
+
+def test_opt_params_mirror_reference_config_reads():
+    from hortimapping_b200.optimizer import opt_params_from_cfg
+    cfg = cfg_of(load_npz("fruit_wild"))
+    # YAML parses `5e-2` as str in the reference's configs; float() casts must accept both
+    cfg["opt"]["weight"]["w_depth"] = "5e-2"
+    p = opt_params_from_cfg(cfg["opt"], iter_offset=3, max_iter=7)
+    assert p.max_iter == 7 and p.iter_offset == 3
+    assert p.w_depth == 0.05 and p.w_mask == 5e-4 and p.w_recon == 1.0 and p.w_codereg == 5e-4
+    assert p.n_depth_samples == 30 and p.log_sdf_occ == 1 and p.occlusion_on == 1 and p.scale_on == 1
+    assert p.lm_on == 1 and p.lm_eye == 0 and p.lm_lambda_0 == 0.1 and p.s_damp == 1e-3
+    assert p.robust_iter == 5 and p.robust_th_recon == 0.01 and p.robust_th_depth == 0.05
+    assert (p.occlusion_th, p.min_valid_sample, p.min_grad_thre) == (0.03, 100, 1e-6)     # loss.py:11
+
+
+def test_frame_selection_matches_reference_linspace():
+    from hortimapping_b200.optimizer import select_frames
+    for n, mx in ((4, 10), (10, 10), (23, 10), (7, 5), (1, 10)):
+        np.testing.assert_array_equal(select_frames(n, mx), np.linspace(0, n - 1, min(mx, n)).astype(np.int32))
+
+
+def test_packed_batch_layout():
+    from hortimapping_b200.optimizer import PackedBatch
+    c = load_npz("fruit_wild")
+    rd = render_data_of(c)
+    rd_t = {k: [torch.from_numpy(a) for a in v] for k, v in rd.items()}          # torch inputs like the reference host
+    pk = PackedBatch([c["points_w"], c["points_w"][:100]], [rd, rd_t], 3, [0.08, 0.07], [False, True])
+    assert pk.n_fruits == 2 and pk.point_offsets.tolist() == [0, 512, 612]
+    assert pk.frame_offsets.tolist() == [0, 3, 6]                                 # 4 frames sub-sampled to 3
+    sel = np.linspace(0, 3, 3).astype(np.int32)
+    for j, idx in enumerate(sel):
+        lo, hi = pk.ray_offsets[j], pk.ray_offsets[j + 1]
+        nfg = rd["rays_fg"][idx].shape[0]
+        assert pk.n_fg[j] == nfg and hi - lo == nfg + rd["rays_bg"][idx].shape[0]
+        np.testing.assert_array_equal(pk.rays[lo:lo + nfg], rd["rays_fg"][idx])   # fg first, then bg (optimizer.py:113)
+        np.testing.assert_array_equal(pk.rays[lo + nfg:hi], rd["rays_bg"][idx])
+        np.testing.assert_array_equal(pk.depth_obs[lo:lo + nfg], rd["depth_fg"][idx])
+        np.testing.assert_array_equal(pk.T_wc[j].reshape(4, 4), rd["T_wc"][idx])
+    np.testing.assert_array_equal(pk.rays[pk.ray_offsets[3]:], pk.rays[:pk.ray_offsets[3]])
+    assert pk.pose_known.tolist() == [0, 1] and pk.cube_radius.dtype == np.float32
+    # empty render data (no matched frame) is representable: the device loop then reports "submap not valid"
+    pk2 = PackedBatch([c["points_w"]], [{k: [] for k in rd}], 10, [0.08], [False])
+    assert pk2.frame_offsets.tolist() == [0, 0] and pk2.rays.shape == (0, 3)
+
+
+def test_marching_tetrahedra_sphere_is_watertight_and_outward():
+    from hortimapping_b200.marching import marching_tetrahedra
+    n = 24
+    g = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    v, f = marching_tetrahedra(np.sqrt(X ** 2 + Y ** 2 + Z ** 2) - 0.6, 0.0, [2 / (n - 1)] * 3)
+    v = v - 1
+    assert np.abs(np.linalg.norm(v, axis=1) - 0.6).max() < 5e-3
+    e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), 1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert np.all(cnt == 2)
+    nrm = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    assert np.all((nrm * v[f].mean(1)).sum(1) > 0)
+    assert abs(0.5 * np.linalg.norm(nrm, axis=1).sum() - 4 * np.pi * 0.36) < 0.05
+    ve, fe = marching_tetrahedra(np.ones((8, 8, 8)), 0.0)
+    assert ve.shape == (0, 3) and fe.shape == (0, 3)
+
+
+def test_force_key_error_dict_and_dropin_module_paths():
+    from hortimapping_b200.mesher import ForceKeyErrorDict
+    d = ForceKeyErrorDict(vertices=1, faces=2)
+    assert d.vertices == 1 and d["faces"] == 2
+    with pytest.raises(KeyError):
+        d.missing
+    from hortimapping_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ("wild_completion", "wild_completion.optimizer", "wild_completion.mesher",
+                                            "wild_completion.loss", "deepsdf", "deepsdf.deep_sdf", "deepsdf.deep_sdf.workspace")}
+    try:
+        dropin.install(None)
+        from wild_completion.optimizer import Optimizer
+        from wild_completion.mesher import MeshExtractor
+        from deepsdf.deep_sdf.workspace import config_decoder, load_latent_vectors
+        import hortimapping_b200.optimizer as ho
+        assert Optimizer is ho.Optimizer and callable(config_decoder) and callable(load_latent_vectors) and MeshExtractor
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_decoder_refuses_to_run_without_gpu():
+    """The product path fails loudly instead of falling back to a CPU implementation."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hortimapping_b200.decoder import Decoder
+    from tests.helpers import pepper_weights
+    W, b, _ = pepper_weights()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Decoder(W, b)
+
+
+def test_shard_ranges_cover_everything():
+    from hortimapping_b200.shard import shard_range
+    for n, w in ((512, 8), (64, 1), (10, 4), (3, 8)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
