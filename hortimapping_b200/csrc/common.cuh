@@ -71,6 +71,7 @@ struct hm_context {
   // tensor-core engine
   uint8_t* d_tc_blob = nullptr;    // pre-swizzled fp16 hi/lo weight stages for all 16 ops
   size_t tc_blob_bytes = 0;
+  int tc_blob_copies = 1;
   hm_tc_plan tc_plan;
   float act_absmax[HM_TC_NOPS_ALL] = {};   // calibration result: max |A operand| per op
   float* d_tc_bias = nullptr;      // [8][512] biases of lin0..7 (lin3 padded with 0)

@@ -25,23 +25,22 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;                 // 128 rows x 64 k x 2 B x {hi, lo}
-constexpr int kTileBytes = 16384;                  // one 128 x 64 fp16 tile
-constexpr int kAChunkBytes = 8192;                 // 64 rows x 64 k x 2 B
-constexpr int kSmemAHi = 0;
-constexpr int kSmemALo = 65536;
+constexpr int kStageBytes = 32768;                 // one weight tile: 256 output features x 64 k x 2 B (hi OR lo)
+constexpr int kAChunkBytes = 16384;                // 128 stacked rows (64 points x {hi, lo}) x 64 k x 2 B
+constexpr int kSmemA = 0;
 constexpr int kSmemStages = 131072;
 constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;   // 229376
 constexpr int kSmemTotal = kSmemBars + 256 + 512;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr int kMaskWordsPerOp = 64 * 16;           // 64 rows x 512 bits
+constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per forward layer
 
 // barrier slots (8 bytes each) inside the barrier block
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_PART_FULL = 10, BAR_PART_EMPTY = 12, BAR_COUNT = 14 };
@@ -49,6 +48,8 @@ enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_PART_FULL = 10, BAR
 struct TcParams {
   hm_tc_plan plan;
   const uint8_t* blob;
+  int64_t blob_bytes;         // size of one copy of the weight blob
+  int32_t blob_copies;        // copies laid out back to back (CTAs spread over them)
   const float* bias;          // [8][512]
   const float* w8;            // [512]
   const float* b8;            // [1]
@@ -89,10 +90,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+  long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// weight stages are multicast to every CTA of the cluster: this CTA fetches 1/C of the stage and the copy
+// lands at the same shared-memory offset in all C CTAs, signalling the same-offset mbarrier in each of them
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -117,6 +137,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit that arrives on the same-offset mbarrier of every CTA in `mask` (frees a multicast weight slot cluster-wide)
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -150,42 +175,71 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-// split 8 consecutive fp32 values (already scaled) into fp16 hi / lo and return them packed for one
-// 16-byte store each.  hi = rn(x) saturated to the finite fp16 range, lo = rn(x - hi).
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, int& sat) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a = x[2 * i], b = x[2 * i + 1];
-    float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
-    sat |= (ac != a) | (bc != b);
-    __half2 hh = __floats2half2_rn(ac, bc);
-    float2 hf = __half22float2(hh);
-    __half2 ll = __floats2half2_rn(ac - hf.x, bc - hf.y);
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+// TMEM -> registers, 16 lanes x 256 bit x 4 repeats (= 32 accumulator columns of 16 rows): thread t receives,
+// per 8-column block e, v[4e+0..1] = (row t/4, columns 8e + 2(t%4) + {0,1}) and v[4e+2..3] = the same columns of
+// row t/4 + 8 (cute SM100_TMEM_LOAD_16dp256b4x: the mma.sync C-fragment layout).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100) and saturating fp16x2 pack
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+      "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+// fp16x2 {lo half = a, hi half = b}, round-to-nearest, saturated to +-65504
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// split a scaled fp32 pair into fp16 hi / lo words; `sat` collects "an element hit the fp16 range"
+__device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo, uint32_t& sat) {
+  hi = pack_h2_sat(v.x, v.y);
+  sat |= __vcmpeq2(hi & 0x7fff7fffu, 0x7bff7bffu);
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&hi));
+  const float2 r = fma2(f, make_float2(-1.f, -1.f), v);
+  lo = pack_h2_sat(r.x, r.y);
 }
 
-// write 32 consecutive columns (local k0 .. k0+31 of chunk `chunk`) of row `row` of the A operand
-__device__ __forceinline__ void store_a32(uint8_t* smem, int chunk, int row, int k0, const float* x, int& sat) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    uint4 hi, lo;
-    split8(x + 8 * u, hi, lo, sat);
-    uint32_t off = (uint32_t)chunk * kAChunkBytes + sw128_offset(row, k0 + 8 * u);
-    *reinterpret_cast<uint4*>(smem + kSmemAHi + off) = hi;
-    *reinterpret_cast<uint4*>(smem + kSmemALo + off) = lo;
-  }
+// A-operand row of point p: the tile stacks the fp16 hi parts and the lo parts of the SAME 64 points as 128 MMA
+// rows, so that one full-rate M = 128 MMA multiplies both by a weight tile.  hi of point p sits on row
+// 32*(p/16) + p%16 and its lo on the row 16 below, i.e. both land in the same TMEM sub-partition.
+__host__ __device__ __forceinline__ int a_row(int p, int part) { return 32 * (p >> 4) + 16 * part + (p & 15); }
+
+// split two scaled fp32 values into packed fp16 hi and lo words (hi = rn(x) saturated to the finite fp16 range,
+// lo = rn(x - hi)) and store them at columns (k, k+1) of point p in chunk `chunk` of the stacked A operand
+__device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int k, float a, float b, int& sat) {
+  const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+  sat |= (ac != a) | (bc != b);
+  const __half2 hh = __floats2half2_rn(ac, bc);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(ac - hf.x, bc - hf.y);
+  uint8_t* base = smem + (uint32_t)chunk * kAChunkBytes;
+  *reinterpret_cast<__half2*>(base + sw128_offset(a_row(p, 0), k)) = hh;
+  *reinterpret_cast<__half2*>(base + sw128_offset(a_row(p, 1), k)) = ll;
 }
 
-// k-chunk consumption order of an 8-chunk op.  An epilogue warp (sub-partition sp, column quarter qsel) owns
-// output columns [256*h + 128*qsel, +128) for its two lane halves h; it finishes the 64-column chunks
-// (2*qsel + j) and (4 + 2*qsel + j) together at step j, so the A operand becomes ready in "pairs"
-// P = 2*j + qsel = {0,4}, {2,6}, {1,5}, {3,7}, and that is the order the MMA warp (and the weight blob) walk K.
-__host__ __device__ __forceinline__ int chunk_of(int pair, int which) { return 2 * (pair & 1) + (pair >> 1) + 4 * which; }
+// k-chunk order of an 8-chunk op.  Epilogue warp group h2 (0/1) owns output columns [128*h2, +128) of each
+// 256-column half and finishes them in four 64-column steps j: chunks {0,1,4,5} (h2 = 0) and {2,3,6,7} (h2 = 1).
+// The A operand therefore becomes ready two chunks per step -- {0,2}, {1,3}, {4,6}, {5,7} -- and that is the
+// order in which the MMA warp (and the weight blob) walk K.
+__host__ __device__ __forceinline__ int chunk_of(int step, int which) { return (step & 1) + 4 * (step >> 1) + 2 * which; }
 
 template <bool kJac>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
@@ -195,12 +249,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
-  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 rows][2 quarters]
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][2 warp groups]
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
-    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), 4);
+    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps);
     for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -217,249 +271,330 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      long long t_empty = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int op = 0; op < kOps; ++op) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t bytes = (uint32_t)o.stage_rows * 128u * 2u;
-          const int nst = o.n_kchunks * o.n_nblocks;
+          const uint32_t bytes = (uint32_t)o.stage_rows * 128u;          // one 64-k fp16 tile
+          const int nst = o.n_kchunks * o.n_nblocks * 2;                 // (chunk, n-half) x {lo, hi}
           const uint8_t* src = P.blob + o.blob_offset;
           for (int s = 0; s < nst; ++s) {
-            mbar_wait(bar(BAR_W_EMPTY + slot), phase ^ 1);
+            mbar_wait_timed(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
             mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
             bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes, bytes, bar(BAR_W_FULL + slot));
             if (++slot == kStages) { slot = 0; phase ^= 1; }
           }
         }
       }
+      if (P.flags) atomicAdd((unsigned long long*)(P.flags + 8), (unsigned long long)t_empty);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The tensor core accumulates fp32 with round-toward-zero (measured on B200: ~ -1e-7 relative per chained
-    // MMA, -9e-6 after the 96 MMAs of one K = 512 layer).  To keep fp32 parity every 64-wide k-chunk gets a
-    // FRESH accumulator (12 MMAs: the two small cross terms first, then hi*hi) in one of two 256-column TMEM
-    // buffers, and the epilogue warps add the chunk partials in registers (fp32 round-to-nearest).
+    // One accumulation group = (k-chunk, 256-column output half): 4 MMAs against the lo weight tile, then 4 against
+    // the hi tile, M = 128 (hi rows and lo rows of 64 points) x N = 256 x K = 16, into a FRESH 256-column TMEM
+    // buffer.  The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA),
+    // so chains are kept to one k-chunk and the epilogue warps add the group partials in fp32 round-to-nearest.
     if (lane == 0) {
       uint32_t slot = 0, phase = 0, op_seq = 0, gseq = 0;
+      long long t_a = 0, t_part = 0, t_w = 0, t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int op = 0; op < kOps; ++op, ++op_seq) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t idesc = make_idesc(HM_TC_TILE_M, o.stage_rows);
-          const uint32_t lo_off = (uint32_t)o.stage_rows * 128u;     // lo tile follows the hi tile inside a stage
-          for (int pair = 0; pair < 4; ++pair) {
-            mbar_wait(bar(BAR_A_READY + pair), op_seq & 1);
+          const uint32_t idesc = make_idesc(128, o.stage_rows);
+          for (int step = 0; step < 4; ++step) {
+            mbar_wait_timed(bar(BAR_A_READY + step), op_seq & 1, t_a);
             tc_fence_after();
-            const int nwhich = (o.n_kchunks == 1) ? (pair == 0 ? 1 : 0) : 2;
-            for (int which = 0; which < nwhich; ++which, ++gseq) {
-              const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(pair, which);
+            const int nwhich = (o.n_kchunks == 1) ? (step == 0 ? 1 : 0) : 2;
+            if (nwhich == 0) continue;
+            for (int nh = 0; nh < o.n_nblocks; ++nh, ++gseq) {
               const uint32_t buf = gseq & 1;
-              mbar_wait(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1);
+              mbar_wait_timed(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1, t_part);
               tc_fence_after();
-              const uint32_t a_hi = smem_base + kSmemAHi + chunk * kAChunkBytes;
-              const uint32_t a_lo = smem_base + kSmemALo + chunk * kAChunkBytes;
-              for (int nb = 0; nb < o.n_nblocks; ++nb) {
-                mbar_wait(bar(BAR_W_FULL + slot), phase);
-                tc_fence_after();
-                const uint32_t w_hi = smem_base + kSmemStages + slot * kStageBytes;
-                const uint32_t w_lo = w_hi + lo_off;
-                const uint32_t d = tmem_base + ((uint32_t)(16 * (nb >> 1)) << 16) + buf * 256 + (nb & 1) * 128;
+              const uint32_t d = tmem_base + buf * 256;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_lo + ks * 32), make_desc(w_hi + ks * 32), idesc, ks ? 1u : 0u);
+              for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
+                for (int which = 0; which < nwhich; ++which) {
+                  const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+                  const uint32_t a_addr = smem_base + kSmemA + chunk * kAChunkBytes;
+                  mbar_wait_timed(bar(BAR_W_FULL + slot), phase, t_w);
+                  tc_fence_after();
+                  const uint32_t w_addr = smem_base + kSmemStages + slot * kStageBytes;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(w_lo + ks * 32), idesc, 1u);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(w_hi + ks * 32), idesc, 1u);
-                umma_commit(bar(BAR_W_EMPTY + slot));
-                if (++slot == kStages) { slot = 0; phase ^= 1; }
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(d, make_desc(a_addr + ks * 32), make_desc(w_addr + ks * 32), idesc, (part | which | ks) ? 1u : 0u);
+                  umma_commit(bar(BAR_W_EMPTY + slot));
+                  if (++slot == kStages) { slot = 0; phase ^= 1; }
+                }
               }
               umma_commit(bar(BAR_PART_FULL + buf));
             }
           }
         }
       }
+      if (P.flags) {
+        atomicAdd((unsigned long long*)(P.flags + 10), (unsigned long long)t_a);
+        atomicAdd((unsigned long long*)(P.flags + 12), (unsigned long long)t_part);
+        atomicAdd((unsigned long long*)(P.flags + 14), (unsigned long long)t_w);
+        atomicAdd((unsigned long long*)(P.flags + 16), (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else {
     // ===================== epilogue warps (8) =====================
-    const int e = warp - 2;
-    const int sp = warp & 3;                 // TMEM sub-partition this warp may read
-    const int qsel = e >> 2;                 // which 128-column quarter pair of the tile this warp owns
-    const int half = lane >> 4;              // lanes 16..31 of a sub-partition hold output columns 256..511
-    const int row = 16 * sp + (lane & 15);   // tile row (M = 64 layout: row r <-> lane 32*(r/16) + r%16)
-    const int col0 = 256 * half + 128 * qsel;   // first global output column of this thread
-    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * qsel;
-    uint32_t* my_masks = P.masks + (size_t)blockIdx.x * 8 * kMaskWordsPerOp + row * 16 + (col0 >> 5);
+    // Warp (sp, h2): TMEM sub-partition sp = warp % 4 holds the hi rows (lanes 0..15) and lo rows (lanes 16..31) of
+    // points 16*sp .. 16*sp+15; warp group h2 owns columns [128*h2, +128) of each 256-column output half.  With the
+    // 16x256b load shape thread t holds points pA = 16*sp + t/4 and pB = pA + 8, columns 8e + 2(t%4) + {0,1}:
+    // the hi-row and lo-row results of one (point, column) arrive in the SAME thread and are summed there.
+    const int e_w = warp - 2;
+    const int sp = warp & 3;
+    const int h2 = e_w >> 2;
+    const int tq = lane & 3;                 // column pair inside an 8-column block
+    const int pA = 16 * sp + (lane >> 2), pB = pA + 8;
+    const uint32_t t_hi = tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * h2;
+    const uint32_t t_lo = t_hi + (16u << 16);
+    uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 4;   // [op][thread][4 words]
     uint32_t op_seq = 0, gseq = 0;
     int sat = 0;
-    auto publish = [&](int j) {              // this warp's chunks (2*qsel + j) and (4 + 2*qsel + j) are written
+    auto publish = [&](int j) {              // this warp's 64-column chunk of step j is written
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_A_READY + 2 * j + qsel));
+      if (lane == 0) mbar_arrive(bar(BAR_A_READY + j));
+    };
+    // Column (within the 512-wide layer) of accumulator pair i = 32*nh + 8*cb + 2*e: 256*nh + 128*h2 + 32*cb + 8*e + 2*tq.
+    // Its A-operand address: chunk 4*nh + 2*h2 + (cb >> 1), 16-byte unit 4*(cb & 1) + e (XOR row & 7), byte 4*tq.
+    auto col_of = [&](int nh, int cb, int e) { return 256 * nh + 128 * h2 + 32 * cb + 8 * e + 2 * tq; };
+    const uint32_t r7 = (uint32_t)(lane >> 2) & 7u;
+    uint8_t* const st_base = smem + kSmemA + (uint32_t)(2 * h2) * kAChunkBytes + 4 * tq;
+    const uint32_t rowA_hi = (uint32_t)(a_row(pA, 0) >> 3) * 1024 + (a_row(pA, 0) & 7) * 128;
+    const uint32_t rowA_lo = rowA_hi + 2048, rowB_hi = rowA_hi + 1024, rowB_lo = rowA_hi + 3072;   // +16 rows / +8 rows / +24 rows
+    uint32_t sat2 = 0;
+    auto store2 = [&](int nh, int cb, int e, float2 va, float2 vb) {
+      const uint32_t off = (uint32_t)(4 * nh + (cb >> 1)) * kAChunkBytes + (((uint32_t)(4 * (cb & 1) + e) ^ r7) << 4);
+      uint32_t ha, la, hb, lb;
+      split2(va, ha, la, sat2);
+      split2(vb, hb, lb, sat2);
+      *reinterpret_cast<uint32_t*>(st_base + off + rowA_hi) = ha;
+      *reinterpret_cast<uint32_t*>(st_base + off + rowA_lo) = la;
+      *reinterpret_cast<uint32_t*>(st_base + off + rowB_hi) = hb;
+      *reinterpret_cast<uint32_t*>(st_base + off + rowB_lo) = lb;
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t grow = tile * HM_TC_TILE_M + row;
-      const bool row_ok = grow < n_rows;
-      const int64_t lrow = row_ok ? grow : (n_rows - 1);
-      // raw input x0 = [latent(32), xyz(3)] of this row (deep_sdf_decoder.py:76-88)
-      const float* lat_src;
-      const float* xyz_src;
-      if (P.rows) { lat_src = P.rows + lrow * HM_IN; xyz_src = lat_src + HM_LATENT; }
-      else { lat_src = P.latents + (size_t)(P.row_latent ? P.row_latent[lrow] : 0) * HM_LATENT; xyz_src = P.xyz + lrow * 3; }
-      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64), written by the qsel = 0 warps
-      {
-        if (qsel == 0) {
-          const float s0 = P.plan.ops[0].in_scale;
-          float x[32];
-          if (half == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = lat_src[i] * s0;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (i < 3) ? xyz_src[i] * s0 : 0.f;
-          }
-          store_a32(smem, 0, row, 32 * half, x, sat);
-        }
-        publish(0);
-        publish(1);
+      const int64_t growA = tile * HM_TC_TILE_M + pA, growB = tile * HM_TC_TILE_M + pB;
+      const bool okA = growA < n_rows, okB = growB < n_rows;
+      const int64_t lrA = okA ? growA : (n_rows - 1), lrB = okB ? growB : (n_rows - 1);
+      // raw input x0 = [latent(32), xyz(3)] of the two points of this thread (deep_sdf_decoder.py:76-88)
+      const float *latA, *xyzA, *latB, *xyzB;
+      if (P.rows) { latA = P.rows + lrA * HM_IN; xyzA = latA + HM_LATENT; latB = P.rows + lrB * HM_IN; xyzB = latB + HM_LATENT; }
+      else {
+        latA = P.latents + (size_t)(P.row_latent ? P.row_latent[lrA] : 0) * HM_LATENT; xyzA = P.xyz + lrA * 3;
+        latB = P.latents + (size_t)(P.row_latent ? P.row_latent[lrB] : 0) * HM_LATENT; xyzB = P.xyz + lrB * 3;
       }
-      float f_sdf = 0.f;
+      auto x0A = [&](int k) { return k < HM_LATENT ? latA[k] : (k < HM_IN ? xyzA[k - HM_LATENT] : 0.f); };
+      auto x0B = [&](int k) { return k < HM_LATENT ? latB[k] : (k < HM_IN ? xyzB[k - HM_LATENT] : 0.f); };
+      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); warp group h2 writes k in [32*h2, +32)
+      {
+        const float s0 = P.plan.ops[0].in_scale;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 32 * h2 + 8 * e + 2 * tq;
+          store_pair(smem, 0, pA, k, x0A(k) * s0, x0A(k + 1) * s0, sat);
+          store_pair(smem, 0, pB, k, x0B(k) * s0, x0B(k + 1) * s0, sat);
+        }
+        for (int j = 0; j < 4; ++j) publish(j);
+      }
+      float fA = 0.f, fB = 0.f;
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op, ++op_seq) {
         const hm_tc_op& o = P.plan.ops[op];
         const float unscale = o.out_unscale;
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
-        // ---- sum the per-chunk partial accumulators in registers (round-to-nearest)
-        float acc[128];
+        const float k_mul = unscale * s_next;
+        const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, warp group 0 only
+        const int nsteps = (o.n_kchunks == 1) ? 1 : 4;
+        // accumulators of this thread, as column pairs: acc[16*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}
+        float2 accA[32], accB[32];
 #pragma unroll
-        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-        const int ngroups = o.n_kchunks;
-        const int nq = (o.stage_rows == 64) ? ((qsel == 0) ? 2 : 0) : 4;      // B0: 64 output columns, all in quarter 0
-#pragma unroll 1
-        for (int g = 0; g < ngroups; ++g, ++gseq) {
+        for (int i = 0; i < 32; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+        uint32_t mA[2] = {0u, 0u}, mB[2] = {0u, 0u};
+        float dotA = 0.f, dotB = 0.f;
+        if (kJac && op >= 8 && op < 15) {
+          const uint4 mw = *reinterpret_cast<const uint4*>(my_masks + (size_t)(14 - op) * kEpiWarps * 32 * 4);   // ReLU mask of h_{l-1}, l = 15 - op
+          mA[0] = mw.x; mA[1] = mw.y; mB[0] = mw.z; mB[1] = mw.w;
+        }
+        // add the partial accumulator of one (step, n-half) group: hi-row and lo-row results meet in this thread
+        auto promote = [&](auto NH) {
+          constexpr int nh = decltype(NH)::value;
           const uint32_t buf = gseq & 1;
           mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
           tc_fence_after();
+          const int ncb = narrow ? (h2 == 0 ? 2 : 0) : 4;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < nq) {
-              float v[32];
-              tmem_ld32(t_lane + buf * 256 + q * 32, v);
+          for (int cb2 = 0; cb2 < 2; ++cb2) {
+            if (2 * cb2 < ncb) {
+              float2 vh[16], vl[16];
+              tmem_ld_16x256b_x4(t_hi + buf * 256 + 64 * cb2, reinterpret_cast<float*>(vh));
+              tmem_ld_16x256b_x4(t_hi + buf * 256 + 64 * cb2 + 32, reinterpret_cast<float*>(vh + 8));
+              tmem_ld_16x256b_x4(t_lo + buf * 256 + 64 * cb2, reinterpret_cast<float*>(vl));
+              tmem_ld_16x256b_x4(t_lo + buf * 256 + 64 * cb2 + 32, reinterpret_cast<float*>(vl + 8));
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+              for (int q = 0; q < 8; ++q) {          // q = 4*(cb & 1) + e; v[2q] = point A pair, v[2q+1] = point B pair
+                const int i = 16 * nh + 8 * cb2 + q;
+                accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
+                accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
+              }
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(BAR_PART_EMPTY + buf));
-        }
-        if (op < 7) {
-          // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next
-          const float* bias = P.bias + op * HM_HIDDEN + col0;
-          const float k_mul = unscale * s_next;
-          uint32_t* mrow = my_masks + op * kMaskWordsPerOp;
+          ++gseq;
+        };
+        const float2 kk = make_float2(k_mul, k_mul), uu = make_float2(unscale, unscale);
+        // turn the finished accumulators of output half nh into the next op's A operand (or the final outputs)
+        auto finalize = [&](auto NH) {
+          constexpr int nh = decltype(NH)::value;
+          if (op < 7) {
+            // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
+            const float* bias = P.bias + op * HM_HIDDEN;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+            for (int jj = 0; jj < 2; ++jj) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int lc = j * 64 + u * 32;
-              float v[32];
-              uint32_t m = 0;
+              for (int cc = 0; cc < 2; ++cc) {
+                const int cb = 2 * jj + cc;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float y = fmaf(acc[lc + i], k_mul, __ldg(bias + lc + i) * s_next);
-                m |= (y > 0.f ? 1u : 0u) << i;
-                v[i] = fmaxf(y, 0.f);
-              }
-              if (op == 3 && col0 + lc + 32 > HM_SKIP_COL) {
-                // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const int k = col0 + lc + i - HM_SKIP_COL;
-                  if (k >= 0) {
-                    v[i] = (k < HM_LATENT ? lat_src[k] : xyz_src[k - HM_LATENT]) * s_next;
-                    m &= ~(1u << i);
+                for (int e = 0; e < 4; ++e) {
+                  const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
+                  const int col = col_of(nh, cb, e);
+                  const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
+                  float2 ya = fma2(accA[i], kk, bz), yb = fma2(accB[i], kk, bz);
+                  mA[nh] |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
+                  mB[nh] |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
+                  ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
+                  if (nh == 1 && op == 3 && col + 1 >= HM_SKIP_COL) {
+                    // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
+                    if (col >= HM_SKIP_COL) { ya.x = x0A(col - HM_SKIP_COL) * s_next; yb.x = x0B(col - HM_SKIP_COL) * s_next; mA[nh] &= ~(1u << bit); mB[nh] &= ~(1u << bit); }
+                    ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next;
+                    mA[nh] &= ~(1u << (bit + 1)); mB[nh] &= ~(1u << (bit + 1));
                   }
+                  store2(nh, cb, e, ya, yb);
                 }
               }
-              if (kJac) mrow[j * 2 + u] = m;
-              store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
+              publish(2 * nh + jj);
             }
-            publish(j);
+          } else if (op == 7) {
+            // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
+            const float* bias = P.bias + 7 * HM_HIDDEN;
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) {
+              const int i = 16 * nh + ii, bit = 2 * ii;
+              const int col = col_of(nh, ii >> 2, ii & 3);
+              const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
+              const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col));
+              const float2 ya = fma2(accA[i], uu, bz), yb = fma2(accB[i], uu, bz);
+              mA[nh] |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
+              mB[nh] |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
+              dotA = fmaf(fmaxf(ya.x, 0.f), wz.x, dotA); dotA = fmaf(fmaxf(ya.y, 0.f), wz.y, dotA);
+              dotB = fmaf(fmaxf(yb.x, 0.f), wz.x, dotB); dotB = fmaf(fmaxf(yb.y, 0.f), wz.y, dotB);
+            }
+          } else if (op < 15) {
+            // ---------------- backward through lin_l (l = 15 - op = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int cb = 2 * jj + cc;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
+                  if (nh == 1 && op == 11) {
+                    const int col = col_of(nh, cb, e);
+                    if (col + 1 >= HM_SKIP_COL) {
+                      // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
+                      // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
+                      if (col >= HM_SKIP_COL) {
+                        if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale);
+                        if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale);
+                      }
+                      if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale);
+                      if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale);
+                    }
+                  }
+                  const float2 sa = make_float2(((mA[nh] >> bit) & 1u) ? k_mul : 0.f, ((mA[nh] >> (bit + 1)) & 1u) ? k_mul : 0.f);
+                  const float2 sb = make_float2(((mB[nh] >> bit) & 1u) ? k_mul : 0.f, ((mB[nh] >> (bit + 1)) & 1u) ? k_mul : 0.f);
+                  store2(nh, cb, e, make_float2(accA[i].x * sa.x, accA[i].y * sa.y), make_float2(accB[i].x * sb.x, accB[i].y * sb.y));
+                }
+              }
+              if (nh == 1 && op == 11 && jj == 1) __threadfence_block();
+              publish(2 * nh + jj);
+            }
           }
+        };
+        // ---- group loop.  Output half 0 is complete one group before half 1, so it is finalized (and its A chunks
+        //      published) while the MMA warp still works on the last group: the next op can start without a bubble.
+#pragma unroll 1
+        for (int st = 0; st < nsteps - 1; ++st) {
+          promote(std::integral_constant<int, 0>{});
+          if (!narrow) promote(std::integral_constant<int, 1>{});
+        }
+        promote(std::integral_constant<int, 0>{});
+        if (op != 15) finalize(std::integral_constant<int, 0>{});
+        if (!narrow) promote(std::integral_constant<int, 1>{});
+        if (op != 15) finalize(std::integral_constant<int, 1>{});
+        if (op < 7) {
+          if (kJac) *reinterpret_cast<uint4*>(my_masks + (size_t)op * kEpiWarps * 32 * 4) = make_uint4(mA[0], mA[1], mB[0], mB[1]);
         } else if (op == 7) {
-          // ---------------- lin7 epilogue + lin8 + tanh (deep_sdf_decoder.py:107-108)
-          const float* bias = P.bias + 7 * HM_HIDDEN + col0;
-          const float* w8 = P.w8 + col0;
-          uint32_t mk[4];
-          float dot = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float y = fmaf(acc[q * 32 + i], unscale, __ldg(bias + q * 32 + i));
-              m |= (y > 0.f ? 1u : 0u) << i;
-              dot = fmaf(fmaxf(y, 0.f), __ldg(w8 + q * 32 + i), dot);
-            }
-            mk[q] = m;
+          dotA += __shfl_xor_sync(0xffffffffu, dotA, 1); dotA += __shfl_xor_sync(0xffffffffu, dotA, 2);
+          dotB += __shfl_xor_sync(0xffffffffu, dotB, 1); dotB += __shfl_xor_sync(0xffffffffu, dotB, 2);
+          if (tq == 0) { dot_scratch[pA * 2 + h2] = dotA; dot_scratch[pB * 2 + h2] = dotB; }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          const float b8 = __ldg(P.b8);
+          fA = tanhf(dot_scratch[pA * 2] + dot_scratch[pA * 2 + 1] + b8);
+          fB = tanhf(dot_scratch[pB * 2] + dot_scratch[pB * 2 + 1] + b8);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (h2 == 0 && tq == 0) {
+            if (okA) P.sdf[growA] = fA;
+            if (okB) P.sdf[growB] = fB;
           }
-          dot += __shfl_xor_sync(0xffffffffu, dot, 16);
-          if (half == 0) dot_scratch[row * 2 + qsel] = dot;
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          f_sdf = tanhf(dot_scratch[row * 2] + dot_scratch[row * 2 + 1] + __ldg(P.b8));
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          if (half == 0 && qsel == 0 && row_ok) P.sdf[grow] = f_sdf;
           if (kJac) {
             // d7 = (1 - f^2) * w8 * relu'(h7): A operand of B7
-            const float coef = (1.f - f_sdf * f_sdf) * s_next;
+            const float cA = (1.f - fA * fA) * s_next, cB = (1.f - fB * fB) * s_next;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 4; ++j) {
+              const int nh = j >> 1;
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int q = j * 2 + u;
-                float v[32];
+              for (int cc = 0; cc < 2; ++cc) {
+                const int cb = 2 * (j & 1) + cc;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = ((mk[q] >> i) & 1u) ? coef * __ldg(w8 + q * 32 + i) : 0.f;
-                store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
+                for (int e = 0; e < 4; ++e) {
+                  const int bit = (8 * cb + 2 * e);
+                  const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col_of(nh, cb, e)));
+                  store2(nh, cb, e, make_float2(((mA[nh] >> bit) & 1u) ? cA * wz.x : 0.f, ((mA[nh] >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
+                         make_float2(((mB[nh] >> bit) & 1u) ? cB * wz.x : 0.f, ((mB[nh] >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
+                }
               }
               publish(j);
             }
           }
-        } else if (op < 15) {
-          // ---------------- backward through lin_l (l = 15 - op = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
-          const int l = 15 - op;
-          const uint32_t* mrow = my_masks + (l - 1) * kMaskWordsPerOp;
-          const float k_mul = unscale * s_next;
-          if (l == 4 && col0 == 384 && row_ok) {
-            // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
-            // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
-            float* jrow = P.jac + grow * HM_IN;
+        } else if (op == 15) {
+          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all owned by warp group 0) + the parked skip gradient
+          if (h2 == 0) {
 #pragma unroll
-            for (int k = 0; k < HM_IN; ++k) __stcg(jrow + k, acc[HM_SKIP_COL - 384 + k] * unscale);
-            __threadfence_block();
-          }
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int lc = j * 64 + u * 32;
-              const uint32_t m = mrow[j * 2 + u];
-              float v[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? acc[lc + i] * k_mul : 0.f;
-              store_a32(smem, 4 * half + 2 * qsel + j, row, u * 32, v, sat);
+            for (int i = 0; i < 8; ++i) {              // nh = 0, cb = 0,1: columns 32*cb + 8*e + 2*tq + {0,1} < 64
+              const int col = 32 * (i >> 2) + 8 * (i & 3) + 2 * tq;
+              if (col < HM_IN) {
+                if (okA) { float* q = P.jac + growA * HM_IN + col; *q = fmaf(accA[i].x, unscale, __ldcg(q)); }
+                if (okB) { float* q = P.jac + growB * HM_IN + col; *q = fmaf(accB[i].x, unscale, __ldcg(q)); }
+              }
+              if (col + 1 < HM_IN) {
+                if (okA) { float* q = P.jac + growA * HM_IN + col + 1; *q = fmaf(accA[i].y, unscale, __ldcg(q)); }
+                if (okB) { float* q = P.jac + growB * HM_IN + col + 1; *q = fmaf(accB[i].y, unscale, __ldcg(q)); }
+              }
             }
-            publish(j);
-          }
-        } else {
-          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all in the half-0 lanes of quarter 0) + skip gradient
-          if (qsel == 0 && half == 0 && row_ok) {
-            float* jrow = P.jac + grow * HM_IN;
-#pragma unroll
-            for (int k = 0; k < HM_IN; ++k) jrow[k] = fmaf(acc[k], unscale, __ldcg(jrow + k));
           }
         }
       }
     }
-    if (sat) atomicAdd(P.flags, 1);
+    if (sat | (int)sat2) atomicAdd(P.flags, 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -518,28 +653,119 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __res
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
 
+// MMA issue-rate microbenchmark: `reps` x 4 chained MMAs of shape M x N x 16 from shared memory; returns cycles.
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int reps, int n_acc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t done_bar;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(M, N);
+    long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+      const uint32_t d = tb + (uint32_t)((rep % n_acc) * N) % 512;
+      for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep >= n_acc || ks) ? 1u : 0u);
+    }
+    long long t1 = clock64();
+    umma_commit(smem_u32(&done_bar));
+    mbar_wait(smem_u32(&done_bar), 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+// L2 -> shared-memory ingest microbenchmark: every CTA streams `n_stages` stages of `bytes` through a 3-slot ring
+// (no MMAs; the consumer frees a slot as soon as it is full), unicast or multicast over the cluster.
+__global__ void __launch_bounds__(64, 1) tc_ingest_kernel(const uint8_t* blob, int64_t blob_bytes, int n_stages, uint32_t bytes, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars_[6];
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const uint32_t sbase = smem_u32(smem), b0 = smem_u32(bars_);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(b0 + 8 * i, 1); mbar_init(b0 + 8 * (3 + i), csize); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+  long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    uint32_t slot = 0, phase = 0;
+    const uint32_t part = bytes / csize;
+    int64_t off = ((int64_t)(blockIdx.x / csize) * 7919 * bytes) % (blob_bytes - bytes);
+    off &= ~int64_t(1023);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_wait(b0 + 8 * (3 + slot), phase ^ 1);
+      mbar_expect_tx(b0 + 8 * slot, bytes);
+      if (csize == 1) bulk_g2s(sbase + slot * bytes, blob + off, bytes, b0 + 8 * slot);
+      else bulk_g2s_multicast(sbase + slot * bytes + crank * part, blob + off + crank * part, part, b0 + 8 * slot, cmask);
+      off += bytes;
+      if (off + bytes > blob_bytes) off = 0;
+      if (++slot == 3) { slot = 0; phase ^= 1; }
+    }
+  } else if (threadIdx.x == 32) {
+    uint32_t slot = 0, phase = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_wait(b0 + 8 * slot, phase);
+      if (csize == 1) mbar_arrive(b0 + 8 * (3 + slot));
+      else {
+        for (uint32_t r = 0; r < csize; ++r) {
+          uint32_t remote;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(b0 + 8 * (3 + slot)), "r"(r));
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+        }
+      }
+      if (++slot == 3) { slot = 0; phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
 // ------------------------------------------------------------------ host side: plan + weight blob
 float pow2_floor(float x) { return std::exp2(std::floor(std::log2(x))); }
 
 __half f2h(float x) { return __float2half_rn(x); }
 
-// Fill one K-major SW128 tile pair (hi then lo) of `rows` x 64 from B(n, k) * scale.
+// Fill one K-major SW128 tile of `rows` x 64 with the fp16 hi (part = 1) or lo (part = 0) half of B(n, k) * scale.
 template <class F>
-void fill_stage(uint8_t* dst, int rows, float scale, F&& get) {
-  uint8_t* hi = dst;
-  uint8_t* lo = dst + (size_t)rows * 128;
+void fill_tile(uint8_t* dst, int rows, float scale, int part, F&& get) {
   for (int n = 0; n < rows; ++n)
     for (int k = 0; k < 64; ++k) {
       float x = get(n, k) * scale;
       __half h = f2h(x);
       __half l = f2h(x - __half2float(h));
-      uint32_t off = sw128_offset(n, k);
-      memcpy(hi + off, &h, 2);
-      memcpy(lo + off, &l, 2);
+      memcpy(dst + sw128_offset(n, k), part ? &h : &l, 2);
     }
 }
 
 }  // namespace
+
+static int hm_tc_cluster_size() {
+  const char* e = getenv("HM_TC_CLUSTER");
+  int c = e ? atoi(e) : 1;
+  return 1;   // weight multicast measured slower than unicast; the kernel is built for cluster size 1
+}
+
+static int hm_tc_blob_copies() {
+  const char* e = getenv("HM_TC_BLOB_COPIES");
+  int c = e ? atoi(e) : 1;
+  return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
 
 int hm_tc_init(hm_context* ctx) {
   // op list: F0..F7 (lin0..lin7), B7..B1, B0
@@ -555,8 +781,8 @@ int hm_tc_init(hm_context* ctx) {
     const int l = fwd ? op : 15 - op;
     hm_tc_op& o = plan.ops[op];
     o.n_kchunks = (op == 0) ? 1 : 8;
-    o.n_nblocks = (op == 15) ? 1 : 4;
-    o.stage_rows = (op == 15) ? 64 : 128;
+    o.n_nblocks = (op == 15) ? 1 : 2;                // 256-column output halves (B0: one 64-column block)
+    o.stage_rows = (op == 15) ? 64 : 256;
     o.pad_ = 0;
     const float amax = std::max(ctx->act_absmax[op], 1e-20f);
     o.in_scale = pow2_floor(1024.f / amax);          // 64x headroom below the fp16 maximum
@@ -565,41 +791,48 @@ int hm_tc_init(hm_context* ctx) {
     o.blob_offset = (int64_t)blob.size();
     const std::vector<float>& W = ctx->h_W[l];
     const int in_dim = ctx->in_dim[l];
-    const size_t stage_bytes = (size_t)o.stage_rows * 128 * 2;
-    const int npairs = (o.n_kchunks == 1) ? 1 : 4;
-    for (int pair = 0; pair < npairs; ++pair)
-      for (int which = 0; which < ((o.n_kchunks == 1) ? 1 : 2); ++which) {
-        const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(pair, which);
-        for (int nb = 0; nb < o.n_nblocks; ++nb) {
-          size_t at = blob.size();
-          blob.resize(at + stage_bytes, 0);
-          fill_stage(blob.data() + at, o.stage_rows, w_scale, [&](int n, int k) -> float {
-            const int gn = nb * o.stage_rows + n, gk = chunk * 64 + k;
-            if (fwd) {                       // B[n][k] = W_l[n][k]
-              if (gk >= in_dim) return 0.f;
-              return W[(size_t)gn * in_dim + gk];
-            }
-            // backward: D[row][i] = sum_o d[row][o] W_l[o][i]  ->  B[n = i][k = o] = W_l[o][i]
-            if (gn >= in_dim) return 0.f;
-            return W[(size_t)gk * in_dim + gn];
-          });
-        }
-      }
+    const size_t tile_bytes = (size_t)o.stage_rows * 128;
+    const int nsteps = (o.n_kchunks == 1) ? 1 : 4;
+    for (int step = 0; step < nsteps; ++step)
+      for (int nh = 0; nh < o.n_nblocks; ++nh)
+        for (int part = 0; part < 2; ++part)           // lo tiles of the step's chunks first, then the hi tiles
+          for (int which = 0; which < ((o.n_kchunks == 1) ? 1 : 2); ++which) {
+            const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+            size_t at = blob.size();
+            blob.resize(at + tile_bytes, 0);
+            fill_tile(blob.data() + at, o.stage_rows, w_scale, part, [&](int n, int k) -> float {
+              const int gn = nh * o.stage_rows + n, gk = chunk * 64 + k;
+              if (fwd) {                       // B[n][k] = W_l[n][k]
+                if (gk >= in_dim) return 0.f;
+                return W[(size_t)gn * in_dim + gk];
+              }
+              // backward: D[row][i] = sum_o d[row][o] W_l[o][i]  ->  B[n = i][k = o] = W_l[o][i]
+              if (gn >= in_dim) return 0.f;
+              return W[(size_t)gk * in_dim + gn];
+            });
+          }
   }
-  if (ctx->d_tc_blob && ctx->tc_blob_bytes != blob.size()) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
-  if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size()));
+  const int copies = hm_tc_blob_copies();
+  if (ctx->d_tc_blob && (ctx->tc_blob_bytes != blob.size() || ctx->tc_blob_copies != copies)) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
+  if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size() * copies));
   ctx->tc_blob_bytes = blob.size();
-  HM_CUDA(cudaMemcpy(ctx->d_tc_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  ctx->tc_blob_copies = copies;
+  for (int c = 0; c < copies; ++c)
+    HM_CUDA(cudaMemcpy(ctx->d_tc_blob + (size_t)c * blob.size(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
   if (!ctx->d_tc_bias) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
-    HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 16));
-    HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 16));
+    HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 32));
+    HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 32));
     HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   }
   std::vector<float> bias(8 * HM_HIDDEN, 0.f);
-  for (int l = 0; l < 8; ++l) memcpy(bias.data() + l * HM_HIDDEN, ctx->h_b[l].data(), sizeof(float) * ctx->h_b[l].size());
+  for (int l = 0; l < 8; ++l) {
+    memcpy(bias.data() + l * HM_HIDDEN, ctx->h_b[l].data(), sizeof(float) * ctx->h_b[l].size());
+    if (l < 7)                                       // the F_l epilogue emits h_l * in_scale(F_{l+1}): fold the scale into the bias
+      for (int c = 0; c < HM_HIDDEN; ++c) bias[l * HM_HIDDEN + c] *= plan.ops[l + 1].in_scale;
+  }
   HM_CUDA(cudaMemcpy(ctx->d_tc_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice));
   return HM_OK;
 }
@@ -620,6 +853,8 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   TcParams P;
   P.plan = ctx->tc_plan;
   P.blob = ctx->d_tc_blob;
+  P.blob_bytes = (int64_t)ctx->tc_blob_bytes;
+  P.blob_copies = ctx->tc_blob_copies;
   P.bias = ctx->d_tc_bias;
   P.w8 = ctx->d_W[8];
   P.b8 = ctx->d_b[8];
@@ -635,11 +870,25 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.flags = ctx->d_tc_flags;
   P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
-  const int grid = (int)std::min<int64_t>(n_tiles, ctx->sm_count);
+  int csize = hm_tc_cluster_size();
+  while (csize > 1 && n_tiles < 2 * csize) csize >>= 1;              // tiny launches: no point in clustering
+  int grid = (int)std::min<int64_t>((n_tiles + csize - 1) / csize * csize, (ctx->sm_count / csize) * csize);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (d_jac)
-    tc_decoder_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(P);
+    HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true>, P));
   else
-    tc_decoder_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(P);
+    HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false>, P));
   ctx->counters.kernel_launches += 1;
   HM_CUDA(cudaGetLastError());
   return HM_OK;
@@ -664,5 +913,61 @@ extern "C" int hm_debug_tc_selftest(hm_context* ctx, const uint16_t* h_A, const 
   HM_CUDA(cudaDeviceSynchronize());
   HM_CUDA(cudaMemcpy(h_out, dO, 128 * 256 * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return HM_OK;
+}
+
+// Debug export: cumulative wait-cycle counters of the producer / MMA threads (summed over CTAs and launches):
+// out[0] producer waiting for a free slot, out[1..3] MMA thread waiting for the A operand / a free partial
+// buffer / a full weight stage, out[4] MMA thread total cycles.  Resets the counters.
+extern "C" int hm_debug_tc_wait_cycles(hm_context* ctx, unsigned long long* out) {
+  HM_CHECK(ctx && out && ctx->d_tc_flags, "hm_debug_tc_wait_cycles: bad argument");
+  HM_CUDA(cudaDeviceSynchronize());
+  HM_CUDA(cudaMemcpy(out, ctx->d_tc_flags + 8, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost));
+  HM_CUDA(cudaMemset(ctx->d_tc_flags + 8, 0, sizeof(unsigned long long) * 5));
+  return HM_OK;
+}
+
+extern "C" int hm_debug_tc_mma_rate(hm_context* ctx, int M, int N, int reps, int n_acc, long long* h_out) {
+  HM_CHECK(ctx && h_out, "hm_debug_tc_mma_rate: bad argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  long long* d = nullptr;
+  HM_CUDA(cudaMalloc(&d, 16));
+  HM_CUDA(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  tc_mma_rate_kernel<<<1, 128, 65536>>>(M, N, reps, n_acc, d);
+  HM_CUDA(cudaGetLastError());
+  HM_CUDA(cudaDeviceSynchronize());
+  HM_CUDA(cudaMemcpy(h_out, d, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return HM_OK;
+}
+
+extern "C" int hm_debug_tc_ingest(hm_context* ctx, int cluster, int n_stages, int bytes, double* h_bytes_per_clk_per_sm, double* h_ms) {
+  HM_CHECK(ctx && ctx->d_tc_blob, "hm_debug_tc_ingest: bad argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  const int grid = (ctx->sm_count / cluster) * cluster;
+  long long* d = nullptr;
+  HM_CUDA(cudaMalloc(&d, sizeof(long long) * grid));
+  HM_CUDA(cudaFuncSetAttribute(tc_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * bytes + 1024));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 3 * bytes + 1024; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEventRecord(e0);
+    HM_CUDA(cudaLaunchKernelEx(&cfg, tc_ingest_kernel, (const uint8_t*)ctx->d_tc_blob, (int64_t)ctx->tc_blob_bytes, n_stages, (uint32_t)bytes, d));
+    cudaEventRecord(e1);
+    HM_CUDA(cudaDeviceSynchronize());
+  }
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> h(grid);
+  HM_CUDA(cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+  double mx = 0; for (long long v : h) mx = std::max(mx, (double)v);
+  *h_bytes_per_clk_per_sm = (double)n_stages * bytes / mx;
+  *h_ms = ms;
+  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HM_OK;
 }
