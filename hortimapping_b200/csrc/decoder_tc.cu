@@ -31,19 +31,23 @@
 
 namespace {
 
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;                 // one weight tile: 256 output features x 64 k x 2 B (hi OR lo)
+constexpr int kWeightRing = 98304;                 // shared memory of the weight ring: 3 x 32 KB (single CTA) or 6 x 16 KB (CTA pair)
+constexpr int kMaxStages = 6;
 constexpr int kAChunkBytes = 16384;                // 128 stacked rows (64 points x {hi, lo}) x 64 k x 2 B
 constexpr int kSmemA = 0;
 constexpr int kSmemStages = 131072;
-constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;   // 229376
+constexpr int kSmemBars = kSmemStages + kWeightRing;             // 229376
 constexpr int kSmemTotal = kSmemBars + 256 + 512;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kCtrlWarps = 4;                      // one full warpgroup: producer, MMA issuer, two idle warps (setmaxnreg is per warpgroup)
+constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
+constexpr int kCtrlRegs = 64, kEpiRegs = 216;      // 128 x 64 + 256 x 216 = 63488 <= 65536 registers per SM
 constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per forward layer
 
 // barrier slots (8 bytes each) inside the barrier block
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_READY = 6, BAR_PART_FULL = 10, BAR_PART_EMPTY = 12, BAR_COUNT = 14 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = kMaxStages, BAR_A_READY = 2 * kMaxStages, BAR_PART_FULL = BAR_A_READY + 4,
+       BAR_PART_EMPTY = BAR_PART_FULL + 2, BAR_COUNT = BAR_PART_EMPTY + 2 };
+static_assert(8 * BAR_COUNT + 4 <= 256, "barrier block overflows into the dot-product scratch");
 
 struct TcParams {
   hm_tc_plan plan;
@@ -90,9 +94,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity);
+template <bool kCluster>
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
   long long t0 = clock64();
-  mbar_wait(bar, parity);
+  if constexpr (kCluster) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
   acc += clock64() - t0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -118,30 +124,95 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// TMEM allocation for a single CTA (CG = 1) or a CTA pair (CG = 2: the same warp of BOTH CTAs executes it and both
+// receive the same column address, cute::TMEM::Allocator2Sm)
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, issued by one thread
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, issued by one thread.  CG = 2: issued by the leader CTA of a pair; each CTA
+// supplies its own 128 rows of A and one half of B's N rows from the same shared-memory offsets, and receives its own
+// 128 rows of D in its own TMEM.
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// mbarrier arrive when all MMAs issued so far by this thread have completed.  CG = 2: the arrive is multicast to the
+// same-offset barrier of both CTAs of the pair (cutlass::arch::umma_arrive_multicast_2x1SM).
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// true in exactly one lane of a fully active warp (cute::elect_one_sync).  The warp-specialised roles run their loops with
+// all 32 lanes (warp-uniform control flow keeps descriptors and addresses in uniform registers) and issue the asynchronous
+// operations -- bulk copies, MMAs, commits -- from the elected lane only.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+// address of `addr` (a shared::cta address of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_rank).  Default semantics, as
+// cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release would cost MEMBAR.ALL.GPU per arrive (measured:
+// it serialised the weight ring), and nothing this thread wrote is read through the generic proxy on the other side --
+// the A operand is published with fence.proxy.async and read by each CTA's own tensor core.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local mbarrier whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "DONE_C:\n\t"
+      "}" ::"r"(bar), "r"(parity)
       : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// commit that arrives on the same-offset mbarrier of every CTA in `mask` (frees a multicast weight slot cluster-wide)
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -189,6 +260,22 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for all outstanding TMEM loads; the loaded registers pass through the statement so that no consumer of `a` / `b`
+// can be scheduled above the wait (the arithmetic below is non-volatile asm and would otherwise be free to move)
+__device__ __forceinline__ void tmem_ld_wait_dep(float2 (&a)[8], float2 (&b)[8]) {
+  uint32_t* x = reinterpret_cast<uint32_t*>(a);
+  uint32_t* y = reinterpret_cast<uint32_t*>(b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(x[8]), "+r"(x[9]),
+                 "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]), "+r"(y[8]), "+r"(y[9]),
+                 "+r"(y[10]), "+r"(y[11]), "+r"(y[12]), "+r"(y[13]), "+r"(y[14]), "+r"(y[15])
+               :
+               : "memory");
+}
 
 // packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100) and saturating fp16x2 pack
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
@@ -208,10 +295,11 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-// split a scaled fp32 pair into fp16 hi / lo words; `sat` collects "an element hit the fp16 range"
+// split a scaled fp32 pair into fp16 hi / lo words; `sat` keeps the running per-half maximum of |hi| (0x7bff = the
+// conversion saturated: the kernel reports HM_STATUS_F16_SATURATED)
 __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo, uint32_t& sat) {
   hi = pack_h2_sat(v.x, v.y);
-  sat |= __vcmpeq2(hi & 0x7fff7fffu, 0x7bff7bffu);
+  sat = __vmaxu2(sat, hi & 0x7fff7fffu);
   const float2 f = __half22float2(*reinterpret_cast<__half2*>(&hi));
   const float2 r = fma2(f, make_float2(-1.f, -1.f), v);
   lo = pack_h2_sat(r.x, r.y);
@@ -241,110 +329,168 @@ __device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int 
 // order in which the MMA warp (and the weight blob) walk K.
 __host__ __device__ __forceinline__ int chunk_of(int step, int which) { return (step & 1) + 4 * (step >> 1) + 2 * which; }
 
-template <bool kJac>
+// Accumulation groups of one op, in issue order.  A group = (k-step, 256-column output half nh).  For an 8-chunk op with
+// two output halves the order is (0,0) (0,1) (1,0) (1,1) (2,0) (3,0) (2,1) (3,1): output half 0 is complete TWO groups
+// before the op ends, so the epilogue warps turn it into the next op's A chunks 0..3 while the tensor core is still busy
+// with half 1, and the next op (whose first four groups only read chunks 0..3) starts without a bubble.
+__host__ __device__ __forceinline__ int groups_of(int n_kchunks, int n_nblocks) { return n_kchunks == 1 ? n_nblocks : 4 * n_nblocks; }
+__host__ __device__ __forceinline__ void group_of(int n_kchunks, int n_nblocks, int g, int& step, int& nh) {
+  if (n_kchunks == 1) { step = 0; nh = g; }
+  else if (n_nblocks == 1) { step = g; nh = 0; }
+  else { step = (0x32321100u >> (4 * g)) & 0xF; nh = (0xCAu >> g) & 1; }
+}
+
+// kPair: the kernel runs as clusters of two CTAs (one TPC).  Each CTA owns a tile of 64 points; the pair issues
+// cta_group::2 MMAs of M = 256 (128 stacked rows per CTA) x N = 256 whose B operand is split between the two CTAs'
+// shared memories, so each CTA streams only HALF of every weight tile from L2 (the single-CTA kernel is bound by the
+// L2 -> shared-memory weight stream: 14.9 MB per 64 points).  CTA rank 0 (the leader) issues all MMAs.
+template <bool kJac, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CG = kPair ? 2 : 1;
+  constexpr int kStages = kPair ? 6 : 3;
+  constexpr int kStageBytes = kWeightRing / kStages;      // 256 / CG output features x 64 k x 2 B (hi OR lo)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp index as a uniform value
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
   float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][2 warp groups]
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;                       // 0 = leader (MMA issuer) of the pair
+  const uint32_t lead_bars = kPair ? mapa_rank(bars, 0) : bars;               // the leader's barrier block (cluster address)
+  auto lead_bar = [&](int i) { return lead_bars + 8u * i; };
+  const int64_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_stride = kPair ? (gridDim.x >> 1) : gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
-    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps); }
+    // W_FULL of the leader also collects the peer's "my half has landed" arrive
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), (kPair && rank == 0) ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
+    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  if (warp == 1) tmem_alloc<CG>(smem_u32((const void*)tmem_ptr_smem), 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();        // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
   const int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
+  const int64_t n_units = kPair ? (n_tiles + 1) / 2 : n_tiles;               // a unit = one tile per CTA of the pair
 
+  if (warp < kCtrlWarps) {
+  // the control warpgroup hands most of its registers to the two epilogue warpgroups (128 accumulators per thread)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
+    // ===================== weight producer (every CTA; a pair member fetches its half of each stage) =====================
+    {
       uint32_t slot = 0, phase = 0;
       long long t_empty = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
         for (int op = 0; op < kOps; ++op) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t bytes = (uint32_t)o.stage_rows * 128u;          // one 64-k fp16 tile
+          const uint32_t bytes = (uint32_t)o.stage_rows * 128u / CG;     // this CTA's rows of one 64-k fp16 tile
           const int nst = o.n_kchunks * o.n_nblocks * 2;                 // (chunk, n-half) x {lo, hi}
-          const uint8_t* src = P.blob + o.blob_offset;
+          const uint8_t* src = P.blob + o.blob_offset + (size_t)rank * bytes;
           for (int s = 0; s < nst; ++s) {
-            mbar_wait_timed(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
-            mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
-            bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes, bytes, bar(BAR_W_FULL + slot));
+            mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
+            if (elect_one()) {
+              mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+              bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes * CG, bytes, bar(BAR_W_FULL + slot));
+            }
+            __syncwarp();
             if (++slot == kStages) { slot = 0; phase ^= 1; }
           }
         }
       }
-      if (P.flags) atomicAdd((unsigned long long*)(P.flags + 8), (unsigned long long)t_empty);
+      if (P.flags && rank == 0 && lane == 0) atomicAdd((unsigned long long*)(P.flags + 8), (unsigned long long)t_empty);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // One accumulation group = (k-chunk, 256-column output half): 4 MMAs against the lo weight tile, then 4 against
-    // the hi tile, M = 128 (hi rows and lo rows of 64 points) x N = 256 x K = 16, into a FRESH 256-column TMEM
-    // buffer.  The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA),
-    // so chains are kept to one k-chunk and the epilogue warps add the group partials in fp32 round-to-nearest.
-    if (lane == 0) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA; whole warp walks the loops, one elected lane issues) =====================
+      // One accumulation group = (k-step = 2 k-chunks, 256-column output half): 8 MMAs against the lo weight tiles, then 8
+      // against the hi tiles, each M = 128 per CTA (hi rows and lo rows of 64 points) x N = 256 x K = 16, into a FRESH
+      // 256-column TMEM buffer.  The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per
+      // chained MMA), so chains are kept short and the epilogue warps add the group partials in fp32 round-to-nearest.
       uint32_t slot = 0, phase = 0, op_seq = 0, gseq = 0;
       long long t_a = 0, t_part = 0, t_w = 0, t_begin = clock64();
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
         for (int op = 0; op < kOps; ++op, ++op_seq) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t idesc = make_idesc(128, o.stage_rows);
-          for (int step = 0; step < 4; ++step) {
-            mbar_wait_timed(bar(BAR_A_READY + step), op_seq & 1, t_a);
+          const uint32_t idesc = make_idesc(128 * CG, o.stage_rows);
+          const int ng = groups_of(o.n_kchunks, o.n_nblocks);
+          const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
+          int steps_ready = 0;
+          if (o.n_kchunks == 1) {                  // F0 reads chunk 0 only; its four A_READY phases are consumed up front
+            for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), op_seq & 1, t_a);
             tc_fence_after();
-            const int nwhich = (o.n_kchunks == 1) ? (step == 0 ? 1 : 0) : 2;
-            if (nwhich == 0) continue;
-            for (int nh = 0; nh < o.n_nblocks; ++nh, ++gseq) {
-              const uint32_t buf = gseq & 1;
-              mbar_wait_timed(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1, t_part);
+          }
+          for (int g = 0; g < ng; ++g, ++gseq) {
+            int step, nh;
+            group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
+            if (steps_ready <= step) {
+              for (; steps_ready <= step; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), op_seq & 1, t_a);
               tc_fence_after();
-              const uint32_t d = tmem_base + buf * 256;
+            }
+            const uint32_t buf = gseq & 1;
+            mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1, t_part);
+            tc_fence_after();
+            const uint32_t d = tmem_base + buf * 256;
 #pragma unroll
-              for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
-                for (int which = 0; which < nwhich; ++which) {
-                  const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
-                  const uint32_t a_addr = smem_base + kSmemA + chunk * kAChunkBytes;
-                  mbar_wait_timed(bar(BAR_W_FULL + slot), phase, t_w);
-                  tc_fence_after();
-                  const uint32_t w_addr = smem_base + kSmemStages + slot * kStageBytes;
+            for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
+              for (int which = 0; which < nwhich; ++which) {
+                const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+                const uint64_t a_desc = make_desc(smem_base + kSmemA + chunk * kAChunkBytes);
+                const uint64_t w_desc = make_desc(smem_base + kSmemStages + slot * kStageBytes);
+                mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_f16(d, make_desc(a_addr + ks * 32), make_desc(w_addr + ks * 32), idesc, (part | which | ks) ? 1u : 0u);
-                  umma_commit(bar(BAR_W_EMPTY + slot));
-                  if (++slot == kStages) { slot = 0; phase ^= 1; }
+                  for (int ks = 0; ks < 4; ++ks)                     // +32 B per 16-wide k step = +2 in the descriptor's address field
+                    umma_f16<CG>(d, a_desc + 2 * ks, w_desc + 2 * ks, idesc, (part | which | ks) ? 1u : 0u);
+                  umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of a pair
+                  if (part == 1 && which == nwhich - 1) umma_commit<CG>(bar(BAR_PART_FULL + buf));
                 }
+                __syncwarp();
+                if (++slot == kStages) { slot = 0; phase ^= 1; }
               }
-              umma_commit(bar(BAR_PART_FULL + buf));
             }
           }
         }
       }
-      if (P.flags) {
+      if (P.flags && lane == 0) {
         atomicAdd((unsigned long long*)(P.flags + 10), (unsigned long long)t_a);
         atomicAdd((unsigned long long*)(P.flags + 12), (unsigned long long)t_part);
         atomicAdd((unsigned long long*)(P.flags + 14), (unsigned long long)t_w);
         atomicAdd((unsigned long long*)(P.flags + 16), (unsigned long long)(clock64() - t_begin));
       }
+    } else if (kPair) {
+      // ===================== peer CTA: tell the leader that this CTA's half of a weight stage has landed =====================
+      uint32_t slot = 0, phase = 0;
+      for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
+        for (int op = 0; op < kOps; ++op) {
+          const hm_tc_op& o = P.plan.ops[op];
+          const int nst = o.n_kchunks * o.n_nblocks * 2;
+          for (int s = 0; s < nst; ++s) {
+            mbar_wait(bar(BAR_W_FULL + slot), phase);
+            if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_W_FULL + slot));
+            __syncwarp();
+            if (++slot == kStages) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     // ===================== epilogue warps (8) =====================
     // Warp (sp, h2): TMEM sub-partition sp = warp % 4 holds the hi rows (lanes 0..15) and lo rows (lanes 16..31) of
     // points 16*sp .. 16*sp+15; warp group h2 owns columns [128*h2, +128) of each 256-column output half.  With the
     // 16x256b load shape thread t holds points pA = 16*sp + t/4 and pB = pA + 8, columns 8e + 2(t%4) + {0,1}:
     // the hi-row and lo-row results of one (point, column) arrive in the SAME thread and are summed there.
-    const int e_w = warp - 2;
+    const int e_w = warp - kCtrlWarps;
     const int sp = warp & 3;
     const int h2 = e_w >> 2;
     const int tq = lane & 3;                 // column pair inside an 8-column block
@@ -354,10 +500,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 4;   // [op][thread][4 words]
     uint32_t op_seq = 0, gseq = 0;
     int sat = 0;
+    long long t_pfull = 0, t_pbody = 0, t_fin = 0;       // debug counters (hm_debug_tc_wait_cycles)
+    const long long t_epi_begin = clock64();
     auto publish = [&](int j) {              // this warp's 64-column chunk of step j is written
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_A_READY + j));
+      if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_A_READY + j)); else mbar_arrive(bar(BAR_A_READY + j)); }
     };
     // Column (within the 512-wide layer) of accumulator pair i = 32*nh + 8*cb + 2*e: 256*nh + 128*h2 + 32*cb + 8*e + 2*tq.
     // Its A-operand address: chunk 4*nh + 2*h2 + (cb >> 1), 16-byte unit 4*(cb & 1) + e (XOR row & 7), byte 4*tq.
@@ -377,7 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       *reinterpret_cast<uint32_t*>(st_base + off + rowB_hi) = hb;
       *reinterpret_cast<uint32_t*>(st_base + off + rowB_lo) = lb;
     };
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
+      const int64_t tile = kPair ? 2 * unit + rank : unit;       // the odd CTA of the last pair may get an all-padding tile
       const int64_t growA = tile * HM_TC_TILE_M + pA, growB = tile * HM_TC_TILE_M + pB;
       const bool okA = growA < n_rows, okB = growB < n_rows;
       const int64_t lrA = okA ? growA : (n_rows - 1), lrB = okB ? growB : (n_rows - 1);
@@ -409,7 +558,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
         const float k_mul = unscale * s_next;
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, warp group 0 only
-        const int nsteps = (o.n_kchunks == 1) ? 1 : 4;
         // accumulators of this thread, as column pairs: acc[16*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}
         float2 accA[32], accB[32];
 #pragma unroll
@@ -424,30 +572,55 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         auto promote = [&](auto NH) {
           constexpr int nh = decltype(NH)::value;
           const uint32_t buf = gseq & 1;
+          const long long tp0 = clock64();
           mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
+          const long long tp1 = clock64();
+          t_pfull += tp1 - tp0;
           tc_fence_after();
-          const int ncb = narrow ? (h2 == 0 ? 2 : 0) : 4;
+          // four 32-column pieces (narrow B0: two, warp group 0 only); piece c+1 is in flight while piece c is added
+          const uint32_t t_h = t_hi + buf * 256, t_l = t_lo + buf * 256;
+          auto load = [&](int c, float2 (&vh)[8], float2 (&vl)[8]) {
+            tmem_ld_16x256b_x4(t_h + 32 * c, reinterpret_cast<float*>(vh));
+            tmem_ld_16x256b_x4(t_l + 32 * c, reinterpret_cast<float*>(vl));
+          };
+          auto add = [&](int c, const float2 (&vh)[8], const float2 (&vl)[8]) {   // v[2q] = point A pair, v[2q+1] = point B pair
 #pragma unroll
-          for (int cb2 = 0; cb2 < 2; ++cb2) {
-            if (2 * cb2 < ncb) {
-              float2 vh[16], vl[16];
-              tmem_ld_16x256b_x4(t_hi + buf * 256 + 64 * cb2, reinterpret_cast<float*>(vh));
-              tmem_ld_16x256b_x4(t_hi + buf * 256 + 64 * cb2 + 32, reinterpret_cast<float*>(vh + 8));
-              tmem_ld_16x256b_x4(t_lo + buf * 256 + 64 * cb2, reinterpret_cast<float*>(vl));
-              tmem_ld_16x256b_x4(t_lo + buf * 256 + 64 * cb2 + 32, reinterpret_cast<float*>(vl + 8));
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {          // q = 4*(cb & 1) + e; v[2q] = point A pair, v[2q+1] = point B pair
-                const int i = 16 * nh + 8 * cb2 + q;
-                accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
-                accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
-              }
+            for (int q = 0; q < 4; ++q) {
+              const int i = 16 * nh + 4 * c + q;
+              accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
+              accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
+            }
+          };
+          auto release = [&]() {               // all TMEM reads of this buffer are complete
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_PART_EMPTY + buf)); else mbar_arrive(bar(BAR_PART_EMPTY + buf)); }
+          };
+          if (narrow && h2 != 0) {
+            release();
+          } else {
+            float2 vh0[8], vl0[8], vh1[8], vl1[8];
+            load(0, vh0, vl0);
+            tmem_ld_wait_dep(vh0, vl0);
+            load(1, vh1, vl1);
+            add(0, vh0, vl0);
+            tmem_ld_wait_dep(vh1, vl1);
+            if (narrow) {
+              release();
+              add(1, vh1, vl1);
+            } else {
+              load(2, vh0, vl0);
+              add(1, vh1, vl1);
+              tmem_ld_wait_dep(vh0, vl0);
+              load(3, vh1, vl1);
+              add(2, vh0, vl0);
+              tmem_ld_wait_dep(vh1, vl1);
+              release();
+              add(3, vh1, vl1);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_PART_EMPTY + buf));
           ++gseq;
+          t_pbody += clock64() - tp1;
         };
         const float2 kk = make_float2(k_mul, k_mul), uu = make_float2(unscale, unscale);
         // turn the finished accumulators of output half nh into the next op's A operand (or the final outputs)
@@ -529,17 +702,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             }
           }
         };
-        // ---- group loop.  Output half 0 is complete one group before half 1, so it is finalized (and its A chunks
-        //      published) while the MMA warp still works on the last group: the next op can start without a bubble.
+        // ---- group loop, in the issue order of group_of().  Output half 0 is complete two groups before the op ends, so
+        //      it is finalized (and its A chunks published) while the tensor core still works on half 1.
+        const std::integral_constant<int, 0> H0{};
+        const std::integral_constant<int, 1> H1{};
+        if (narrow) {
 #pragma unroll 1
-        for (int st = 0; st < nsteps - 1; ++st) {
-          promote(std::integral_constant<int, 0>{});
-          if (!narrow) promote(std::integral_constant<int, 1>{});
+          for (int st = 0; st < 4; ++st) promote(H0);
+        } else {
+          const bool wide = (o.n_kchunks != 1);
+          if (wide) {
+#pragma unroll 1
+            for (int st = 0; st < 2; ++st) { promote(H0); promote(H1); }
+            promote(H0);
+          }
+          promote(H0);
+          long long tf0 = clock64();
+          finalize(H0);
+          t_fin += clock64() - tf0;
+          if (wide) promote(H1);
+          promote(H1);
+          tf0 = clock64();
+          finalize(H1);
+          t_fin += clock64() - tf0;
         }
-        promote(std::integral_constant<int, 0>{});
-        if (op != 15) finalize(std::integral_constant<int, 0>{});
-        if (!narrow) promote(std::integral_constant<int, 1>{});
-        if (op != 15) finalize(std::integral_constant<int, 1>{});
         if (op < 7) {
           if (kJac) *reinterpret_cast<uint4*>(my_masks + (size_t)op * kEpiWarps * 32 * 4) = make_uint4(mA[0], mA[1], mB[0], mB[1]);
         } else if (op == 7) {
@@ -594,13 +780,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         }
       }
     }
-    if (sat | (int)sat2) atomicAdd(P.flags, 1);
+    if (sat | (int)((sat2 & 0xffffu) >= 0x7bffu) | (int)((sat2 >> 16) >= 0x7bffu)) atomicAdd(P.flags, 1);
+    if (P.flags && e_w == 0 && lane == 0) {
+      atomicAdd((unsigned long long*)(P.flags + 18 + 8 * rank), (unsigned long long)t_pfull);
+      atomicAdd((unsigned long long*)(P.flags + 20 + 8 * rank), (unsigned long long)t_pbody);
+      atomicAdd((unsigned long long*)(P.flags + 22 + 8 * rank), (unsigned long long)t_fin);
+      atomicAdd((unsigned long long*)(P.flags + 24 + 8 * rank), (unsigned long long)(clock64() - t_epi_begin));
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();        // the peer's TMEM / shared memory stay valid until both CTAs are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc<CG>(tmem_base, 512);
   }
 }
 
@@ -618,7 +811,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __res
   for (int i = threadIdx.x; i < 64 * 64; i += 128) *reinterpret_cast<__half*>(smem + sw128_offset(i / 64, i % 64)) = A[i];
   for (int i = threadIdx.x; i < 128 * 64; i += 128) *reinterpret_cast<__half*>(smem + 8192 + sw128_offset(i / 64, i % 64)) = B[i];
   if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tmem_slot), 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -638,8 +831,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __res
     const uint32_t idesc = make_idesc(64, 128);
     const uint32_t d = tb + ((uint32_t)lane_off << 16) + col_off;
     for (int rep = 0; rep < repeats; ++rep)
-      for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep | ks) ? 1u : 0u);
-    umma_commit(smem_u32(&done_bar));
+      for (int ks = 0; ks < 4; ++ks) umma_f16<1>(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep | ks) ? 1u : 0u);
+    umma_commit<1>(smem_u32(&done_bar));
   }
   mbar_wait(smem_u32(&done_bar), 0);
   tc_fence_after();
@@ -650,7 +843,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const __half* __res
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tb, 512); }
 }
 
 // MMA issue-rate microbenchmark: `reps` x 4 chained MMAs of shape M x N x 16 from shared memory; returns cycles.
@@ -662,7 +855,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int r
   const uint32_t sa = smem_u32(smem), sb = sa + 16384;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
   if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tmem_slot), 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -673,10 +866,10 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int r
     long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep) {
       const uint32_t d = tb + (uint32_t)((rep % n_acc) * N) % 512;
-      for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep >= n_acc || ks) ? 1u : 0u);
+      for (int ks = 0; ks < 4; ++ks) umma_f16<1>(d, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep >= n_acc || ks) ? 1u : 0u);
     }
     long long t1 = clock64();
-    umma_commit(smem_u32(&done_bar));
+    umma_commit<1>(smem_u32(&done_bar));
     mbar_wait(smem_u32(&done_bar), 0);
     long long t2 = clock64();
     out[0] = t1 - t0;
@@ -684,7 +877,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int r
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tb, 512); }
 }
 
 // L2 -> shared-memory ingest microbenchmark: every CTA streams `n_stages` stages of `bytes` through a 3-slot ring
@@ -755,10 +948,11 @@ void fill_tile(uint8_t* dst, int rows, float scale, int part, F&& get) {
 
 }  // namespace
 
-static int hm_tc_cluster_size() {
-  const char* e = getenv("HM_TC_CLUSTER");
-  int c = e ? atoi(e) : 1;
-  return 1;   // weight multicast measured slower than unicast; the kernel is built for cluster size 1
+// CTA-pair mode (cta_group::2 MMAs, weights split across the pair) is the product path; HM_TC_PAIR=0 selects the
+// single-CTA variant of the same kernel for A/B measurements.
+static bool hm_tc_pair_mode() {
+  const char* e = getenv("HM_TC_PAIR");
+  return !(e && atoi(e) == 0);
 }
 
 static int hm_tc_blob_copies() {
@@ -792,9 +986,9 @@ int hm_tc_init(hm_context* ctx) {
     const std::vector<float>& W = ctx->h_W[l];
     const int in_dim = ctx->in_dim[l];
     const size_t tile_bytes = (size_t)o.stage_rows * 128;
-    const int nsteps = (o.n_kchunks == 1) ? 1 : 4;
-    for (int step = 0; step < nsteps; ++step)
-      for (int nh = 0; nh < o.n_nblocks; ++nh)
+    for (int g = 0; g < groups_of(o.n_kchunks, o.n_nblocks); ++g) {    // stages in the MMA warp's consumption order
+      int step, nh;
+      group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
         for (int part = 0; part < 2; ++part)           // lo tiles of the step's chunks first, then the hi tiles
           for (int which = 0; which < ((o.n_kchunks == 1) ? 1 : 2); ++which) {
             const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
@@ -811,6 +1005,7 @@ int hm_tc_init(hm_context* ctx) {
               return W[(size_t)gk * in_dim + gn];
             });
           }
+    }
   }
   const int copies = hm_tc_blob_copies();
   if (ctx->d_tc_blob && (ctx->tc_blob_bytes != blob.size() || ctx->tc_blob_copies != copies)) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
@@ -822,10 +1017,12 @@ int hm_tc_init(hm_context* ctx) {
   if (!ctx->d_tc_bias) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
-    HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 32));
-    HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 32));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 64));
+    HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 64));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   }
   std::vector<float> bias(8 * HM_HIDDEN, 0.f);
   for (int l = 0; l < 8; ++l) {
@@ -870,9 +1067,10 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.flags = ctx->d_tc_flags;
   P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
-  int csize = hm_tc_cluster_size();
-  while (csize > 1 && n_tiles < 2 * csize) csize >>= 1;              // tiny launches: no point in clustering
-  int grid = (int)std::min<int64_t>((n_tiles + csize - 1) / csize * csize, (ctx->sm_count / csize) * csize);
+  const bool pair = hm_tc_pair_mode();
+  const int csize = pair ? 2 : 1;
+  const int64_t n_units = (n_tiles + csize - 1) / csize;             // a unit = one 64-row tile per CTA of the cluster
+  const int grid = (int)std::min<int64_t>(n_units, ctx->sm_count / csize) * csize;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -885,10 +1083,13 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (d_jac)
-    HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true>, P));
-  else
-    HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false>, P));
+  if (pair) {
+    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, true>, P));
+    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, true>, P));
+  } else {
+    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, false>, P));
+    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, false>, P));
+  }
   ctx->counters.kernel_launches += 1;
   HM_CUDA(cudaGetLastError());
   return HM_OK;
@@ -918,12 +1119,14 @@ extern "C" int hm_debug_tc_selftest(hm_context* ctx, const uint16_t* h_A, const 
 
 // Debug export: cumulative wait-cycle counters of the producer / MMA threads (summed over CTAs and launches):
 // out[0] producer waiting for a free slot, out[1..3] MMA thread waiting for the A operand / a free partial
-// buffer / a full weight stage, out[4] MMA thread total cycles.  Resets the counters.
+// buffer / a full weight stage, out[4] MMA thread total cycles; out[5..8] first epilogue warp of the leader (or single)
+// CTAs: waiting for a partial accumulator, adding it, finalizing, total; out[9..12] the same for the peer CTAs.
+// Resets the counters.
 extern "C" int hm_debug_tc_wait_cycles(hm_context* ctx, unsigned long long* out) {
   HM_CHECK(ctx && out && ctx->d_tc_flags, "hm_debug_tc_wait_cycles: bad argument");
   HM_CUDA(cudaDeviceSynchronize());
-  HM_CUDA(cudaMemcpy(out, ctx->d_tc_flags + 8, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost));
-  HM_CUDA(cudaMemset(ctx->d_tc_flags + 8, 0, sizeof(unsigned long long) * 5));
+  HM_CUDA(cudaMemcpy(out, ctx->d_tc_flags + 8, sizeof(unsigned long long) * 13, cudaMemcpyDeviceToHost));
+  HM_CUDA(cudaMemset(ctx->d_tc_flags + 8, 0, sizeof(unsigned long long) * 13));
   return HM_OK;
 }
 
