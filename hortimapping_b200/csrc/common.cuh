@@ -78,6 +78,7 @@ struct hm_context {
   float* d_w8 = nullptr;           // [512] lin8 weight, d_b8 scalar in d_b[8]
   uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
   int32_t* d_tc_flags = nullptr;   // saturation counter etc.
+  uint32_t* d_tc_trace = nullptr;  // debug timeline (hm_debug_tc_trace)
   // grow-only workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;

@@ -67,6 +67,7 @@ struct TcParams {
   float* jac;
   uint32_t* masks;            // [grid][8][64][16]
   int32_t* flags;             // [0] = saturation count
+  uint32_t* trace;            // debug timeline of CTA 0 / 1 (hm_debug_tc_trace) or null
   float b0_in_scale_dummy;
 };
 
@@ -361,6 +362,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t lead_bars = kPair ? mapa_rank(bars, 0) : bars;               // the leader's barrier block (cluster address)
   auto lead_bar = [&](int i) { return lead_bars + 8u * i; };
   const int64_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_stride = kPair ? (gridDim.x >> 1) : gridDim.x;
+  // debug timeline: (code << 24 | op << 16 | index, clock) pairs of the first CTA (pair); region 0 = MMA issuer,
+  // 1 / 2 = first epilogue warp of the leader / peer CTA
+  constexpr uint32_t kTraceCap = 8192;
+  const bool tracing = P.trace != nullptr && blockIdx.x < (kPair ? 2 : 1);
+  uint32_t trace_n = 0;
+  auto trace = [&](int region, uint32_t code, uint32_t op, uint32_t idx) {
+    if (tracing && trace_n < kTraceCap) {
+      uint32_t* t = P.trace + (size_t)region * kTraceCap * 2 + 2 * trace_n;
+      t[0] = (code << 24) | (op << 16) | idx;
+      t[1] = (uint32_t)clock64();
+      ++trace_n;
+    }
+  };
 
   if (threadIdx.x == 0) {
     // W_FULL of the leader also collects the peer's "my half has landed" arrive
@@ -375,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   if constexpr (kPair) cluster_sync_all();        // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (lane == 0 && (warp == 1 || warp == kCtrlWarps)) trace(warp == 1 ? 0 : 1 + rank, 0, 0, 0);     // common time origin
 
   const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
   const int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
@@ -435,8 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               tc_fence_after();
             }
             const uint32_t buf = gseq & 1;
+            if (lane == 0) trace(0, 1, op, g);
             mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1, t_part);
             tc_fence_after();
+            if (lane == 0) trace(0, 2, op, g);
             const uint32_t d = tmem_base + buf * 256;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
@@ -457,6 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 if (++slot == kStages) { slot = 0; phase ^= 1; }
               }
             }
+            if (lane == 0) trace(0, 3, op, g);
           }
         }
       }
@@ -551,6 +569,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         for (int j = 0; j < 4; ++j) publish(j);
       }
       float fA = 0.f, fB = 0.f;
+      // Accumulators of this thread, as column pairs: acc[16*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}.  They and
+      // the ReLU bits live across op boundaries: the last quarter of an op (output half 1, cb = 2,3) is finalized only after
+      // the first partial of the NEXT op has been collected (schedule below), so that neither TMEM buffer waits for it.
+      float2 accA[32], accB[32];
+      uint32_t m0A = 0u, m0B = 0u, m1A = 0u, m1B = 0u;   // ReLU bits (half 0 | half 1) x (point A | point B) of the current op
+      uint32_t pmA = 0u, pmB = 0u;                       // half-1 bits of the previous op, for its deferred quarter
+      float dotA = 0.f, dotB = 0.f;
+      const std::integral_constant<int, 0> I0{};
+      const std::integral_constant<int, 1> I1{};
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op, ++op_seq) {
         const hm_tc_op& o = P.plan.ops[op];
@@ -558,25 +585,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
         const float k_mul = unscale * s_next;
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, warp group 0 only
-        // accumulators of this thread, as column pairs: acc[16*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}
-        float2 accA[32], accB[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
-        uint32_t mA[2] = {0u, 0u}, mB[2] = {0u, 0u};
-        float dotA = 0.f, dotB = 0.f;
+        const bool wide = (o.n_kchunks != 1);
+        const bool has_pending = (op != 0 && op != 8);   // the previous op left its last quarter to this one
+        const bool defer = (op != 7 && op != 15);        // ... and this op leaves its own to the next
+        pmA = m1A; pmB = m1B;
+        m0A = m0B = m1A = m1B = 0u;
         if (kJac && op >= 8 && op < 15) {
           const uint4 mw = *reinterpret_cast<const uint4*>(my_masks + (size_t)(14 - op) * kEpiWarps * 32 * 4);   // ReLU mask of h_{l-1}, l = 15 - op
-          mA[0] = mw.x; mA[1] = mw.y; mB[0] = mw.z; mB[1] = mw.w;
+          m0A = mw.x; m1A = mw.y; m0B = mw.z; m1B = mw.w;
         }
-        // add the partial accumulator of one (step, n-half) group: hi-row and lo-row results meet in this thread
-        auto promote = [&](auto NH) {
+        // collect the partial accumulator of one (step, n-half) group: hi-row and lo-row results meet in this thread.
+        // FIRST: the group opens the op for this output half (overwrite instead of accumulate).
+        auto promote = [&](auto NH, auto FIRST) {
           constexpr int nh = decltype(NH)::value;
+          constexpr bool first = decltype(FIRST)::value != 0;
           const uint32_t buf = gseq & 1;
           const long long tp0 = clock64();
           mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
           const long long tp1 = clock64();
           t_pfull += tp1 - tp0;
           tc_fence_after();
+          if (e_w == 0 && lane == 0) trace(1 + rank, 10, op, gseq & 0xffff);
           // four 32-column pieces (narrow B0: two, warp group 0 only); piece c+1 is in flight while piece c is added
           const uint32_t t_h = t_hi + buf * 256, t_l = t_lo + buf * 256;
           auto load = [&](int c, float2 (&vh)[8], float2 (&vl)[8]) {
@@ -587,8 +616,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = 16 * nh + 4 * c + q;
-              accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
-              accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
+              if constexpr (first) {
+                accA[i] = add2(vh[2 * q], vl[2 * q]);
+                accB[i] = add2(vh[2 * q + 1], vl[2 * q + 1]);
+              } else {
+                accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
+                accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
+              }
             }
           };
           auto release = [&]() {               // all TMEM reads of this buffer are complete
@@ -621,113 +655,124 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           }
           ++gseq;
           t_pbody += clock64() - tp1;
+          if (e_w == 0 && lane == 0) trace(1 + rank, 12, op, gseq & 0xffff);
         };
-        const float2 kk = make_float2(k_mul, k_mul), uu = make_float2(unscale, unscale);
-        // turn the finished accumulators of output half nh into the next op's A operand (or the final outputs)
-        auto finalize = [&](auto NH) {
-          constexpr int nh = decltype(NH)::value;
-          if (op < 7) {
+        // Turn one finished quarter (output half nh, column blocks cb = 2*jj, 2*jj+1) of op `opx` into the next op's A operand
+        // (k-step 2*nh + jj) or the final outputs.  kClass: 0 = any op, 1 = opx is a hidden layer (forward or backward, the
+        // deferred quarter), 2 = opx is lin7.
+        auto fin_piece = [&](auto NH, auto JJ, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x,
+                             uint32_t& mA_, uint32_t& mB_) {
+          constexpr int nh = decltype(NH)::value, jj = decltype(JJ)::value, kClass = decltype(CLASS)::value;
+          const long long tf0 = clock64();
+          if (e_w == 0 && lane == 0) trace(1 + rank, 13, opx, 2 * nh + jj);
+          if (kClass != 2 && opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
-            const float* bias = P.bias + op * HM_HIDDEN;
+            const float* bias = P.bias + opx * HM_HIDDEN;
+            const float2 kk = make_float2(k_mul_x, k_mul_x);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
+            for (int cc = 0; cc < 2; ++cc) {
+              const int cb = 2 * jj + cc;
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const int cb = 2 * jj + cc;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
-                  const int col = col_of(nh, cb, e);
-                  const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
-                  float2 ya = fma2(accA[i], kk, bz), yb = fma2(accB[i], kk, bz);
-                  mA[nh] |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
-                  mB[nh] |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
-                  ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                  if (nh == 1 && op == 3 && col + 1 >= HM_SKIP_COL) {
-                    // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
-                    if (col >= HM_SKIP_COL) { ya.x = x0A(col - HM_SKIP_COL) * s_next; yb.x = x0B(col - HM_SKIP_COL) * s_next; mA[nh] &= ~(1u << bit); mB[nh] &= ~(1u << bit); }
-                    ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next;
-                    mA[nh] &= ~(1u << (bit + 1)); mB[nh] &= ~(1u << (bit + 1));
-                  }
-                  store2(nh, cb, e, ya, yb);
+              for (int e = 0; e < 4; ++e) {
+                const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
+                const int col = col_of(nh, cb, e);
+                const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
+                float2 ya = fma2(accA[i], kk, bz), yb = fma2(accB[i], kk, bz);
+                mA_ |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
+                mB_ |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
+                ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
+                if (nh == 1 && jj == 1 && opx == 3 && col + 1 >= HM_SKIP_COL) {
+                  // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
+                  if (col >= HM_SKIP_COL) { ya.x = x0A(col - HM_SKIP_COL) * s_next_x; yb.x = x0B(col - HM_SKIP_COL) * s_next_x; mA_ &= ~(1u << bit); mB_ &= ~(1u << bit); }
+                  ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next_x; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next_x;
+                  mA_ &= ~(1u << (bit + 1)); mB_ &= ~(1u << (bit + 1));
                 }
+                store2(nh, cb, e, ya, yb);
               }
-              publish(2 * nh + jj);
             }
-          } else if (op == 7) {
+            publish(2 * nh + jj);
+          } else if (kClass != 1 && opx == 7) {
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
             const float* bias = P.bias + 7 * HM_HIDDEN;
+            const float2 uu = make_float2(unscale_x, unscale_x);
 #pragma unroll
-            for (int ii = 0; ii < 16; ++ii) {
+            for (int ii = 8 * jj; ii < 8 * jj + 8; ++ii) {
               const int i = 16 * nh + ii, bit = 2 * ii;
               const int col = col_of(nh, ii >> 2, ii & 3);
               const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
               const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col));
               const float2 ya = fma2(accA[i], uu, bz), yb = fma2(accB[i], uu, bz);
-              mA[nh] |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
-              mB[nh] |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
+              mA_ |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
+              mB_ |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
               dotA = fmaf(fmaxf(ya.x, 0.f), wz.x, dotA); dotA = fmaf(fmaxf(ya.y, 0.f), wz.y, dotA);
               dotB = fmaf(fmaxf(yb.x, 0.f), wz.x, dotB); dotB = fmaf(fmaxf(yb.y, 0.f), wz.y, dotB);
             }
-          } else if (op < 15) {
-            // ---------------- backward through lin_l (l = 15 - op = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
+          } else if (kClass != 2 && opx > 7 && opx < 15) {
+            // ---------------- backward through lin_l (l = 15 - opx = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
+            for (int cc = 0; cc < 2; ++cc) {
+              const int cb = 2 * jj + cc;
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const int cb = 2 * jj + cc;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
-                  if (nh == 1 && op == 11) {
-                    const int col = col_of(nh, cb, e);
-                    if (col + 1 >= HM_SKIP_COL) {
-                      // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
-                      // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
-                      if (col >= HM_SKIP_COL) {
-                        if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale);
-                        if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale);
-                      }
-                      if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale);
-                      if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale);
+              for (int e = 0; e < 4; ++e) {
+                const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
+                if (nh == 1 && jj == 1 && opx == 11) {
+                  const int col = col_of(nh, cb, e);
+                  if (col + 1 >= HM_SKIP_COL) {
+                    // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
+                    // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
+                    if (col >= HM_SKIP_COL) {
+                      if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale_x);
+                      if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale_x);
                     }
+                    if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale_x);
+                    if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale_x);
                   }
-                  const float2 sa = make_float2(((mA[nh] >> bit) & 1u) ? k_mul : 0.f, ((mA[nh] >> (bit + 1)) & 1u) ? k_mul : 0.f);
-                  const float2 sb = make_float2(((mB[nh] >> bit) & 1u) ? k_mul : 0.f, ((mB[nh] >> (bit + 1)) & 1u) ? k_mul : 0.f);
-                  store2(nh, cb, e, make_float2(accA[i].x * sa.x, accA[i].y * sa.y), make_float2(accB[i].x * sb.x, accB[i].y * sb.y));
                 }
+                const float2 sa = make_float2(((mA_ >> bit) & 1u) ? k_mul_x : 0.f, ((mA_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
+                const float2 sb = make_float2(((mB_ >> bit) & 1u) ? k_mul_x : 0.f, ((mB_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
+                store2(nh, cb, e, make_float2(accA[i].x * sa.x, accA[i].y * sa.y), make_float2(accB[i].x * sb.x, accB[i].y * sb.y));
               }
-              if (nh == 1 && op == 11 && jj == 1) __threadfence_block();
-              publish(2 * nh + jj);
             }
+            if (nh == 1 && jj == 1 && opx == 11) __threadfence_block();
+            publish(2 * nh + jj);
           }
+          t_fin += clock64() - tf0;
+          if (e_w == 0 && lane == 0) trace(1 + rank, 14, opx, 2 * nh + jj);
         };
-        // ---- group loop, in the issue order of group_of().  Output half 0 is complete two groups before the op ends, so
-        //      it is finalized (and its A chunks published) while the tensor core still works on half 1.
-        const std::integral_constant<int, 0> H0{};
-        const std::integral_constant<int, 1> H1{};
+        // ---- Schedule of one op (groups in the issue order of group_of(); P = promote, F(nh, jj) = finalize a quarter):
+        //        P(0,0) [F'(1,1) of the previous op] P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0,0) P(2,1) F(0,1) P(3,1) F(1,0)
+        //      Output half 0 is complete two groups before the op ends; finalizing is cut into quarters that alternate
+        //      with the promotions, so a TMEM buffer is never held for longer than one quarter and the tensor core runs on.
+        promote(I0, I1);
+        if (has_pending) {
+          const float q_unscale = P.plan.ops[op - 1].out_unscale;
+          fin_piece(I1, I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pmA, pmB);
+          if (kJac && op - 1 < 7) {
+            uint32_t* mw = my_masks + (size_t)(op - 1) * kEpiWarps * 32 * 4;
+            mw[1] = pmA; mw[3] = pmB;
+          }
+        }
         if (narrow) {
 #pragma unroll 1
-          for (int st = 0; st < 4; ++st) promote(H0);
+          for (int st = 0; st < 3; ++st) promote(I0, I0);
         } else {
-          const bool wide = (o.n_kchunks != 1);
           if (wide) {
-#pragma unroll 1
-            for (int st = 0; st < 2; ++st) { promote(H0); promote(H1); }
-            promote(H0);
+            promote(I1, I1); promote(I0, I0); promote(I1, I0); promote(I0, I0); promote(I0, I0);
+          } else {
+            promote(I1, I1);       // F0: both output halves read A chunk 0 -- collect both before it is overwritten
           }
-          promote(H0);
-          long long tf0 = clock64();
-          finalize(H0);
-          t_fin += clock64() - tf0;
-          if (wide) promote(H1);
-          promote(H1);
-          tf0 = clock64();
-          finalize(H1);
-          t_fin += clock64() - tf0;
+          fin_piece(I0, I0, I0, op, k_mul, unscale, s_next, m0A, m0B);
+          if (wide) promote(I1, I0);
+          fin_piece(I0, I1, I0, op, k_mul, unscale, s_next, m0A, m0B);
+          if (wide) promote(I1, I0);
+          fin_piece(I1, I0, I0, op, k_mul, unscale, s_next, m1A, m1B);
+          if (!defer) fin_piece(I1, I1, std::integral_constant<int, 2>{}, op, k_mul, unscale, s_next, m1A, m1B);
         }
         if (op < 7) {
-          if (kJac) *reinterpret_cast<uint4*>(my_masks + (size_t)op * kEpiWarps * 32 * 4) = make_uint4(mA[0], mA[1], mB[0], mB[1]);
+          if (kJac) {              // half-0 words now, half-1 words after the deferred quarter
+            uint32_t* mw = my_masks + (size_t)op * kEpiWarps * 32 * 4;
+            mw[0] = m0A; mw[2] = m0B;
+          }
         } else if (op == 7) {
           dotA += __shfl_xor_sync(0xffffffffu, dotA, 1); dotA += __shfl_xor_sync(0xffffffffu, dotA, 2);
           dotB += __shfl_xor_sync(0xffffffffu, dotB, 1); dotB += __shfl_xor_sync(0xffffffffu, dotB, 2);
@@ -737,6 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           fA = tanhf(dot_scratch[pA * 2] + dot_scratch[pA * 2 + 1] + b8);
           fB = tanhf(dot_scratch[pB * 2] + dot_scratch[pB * 2 + 1] + b8);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          dotA = dotB = 0.f;
           if (h2 == 0 && tq == 0) {
             if (okA) P.sdf[growA] = fA;
             if (okB) P.sdf[growB] = fB;
@@ -747,6 +793,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int nh = j >> 1;
+              const uint32_t mA_ = nh ? m1A : m0A, mB_ = nh ? m1B : m0B;
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
                 const int cb = 2 * (j & 1) + cc;
@@ -754,8 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 for (int e = 0; e < 4; ++e) {
                   const int bit = (8 * cb + 2 * e);
                   const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col_of(nh, cb, e)));
-                  store2(nh, cb, e, make_float2(((mA[nh] >> bit) & 1u) ? cA * wz.x : 0.f, ((mA[nh] >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
-                         make_float2(((mB[nh] >> bit) & 1u) ? cB * wz.x : 0.f, ((mB[nh] >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
+                  store2(nh, cb, e, make_float2(((mA_ >> bit) & 1u) ? cA * wz.x : 0.f, ((mA_ >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
+                         make_float2(((mB_ >> bit) & 1u) ? cB * wz.x : 0.f, ((mB_ >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
                 }
               }
               publish(j);
@@ -1039,6 +1086,8 @@ void hm_tc_free(hm_context* ctx) {
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
   if (ctx->d_tc_masks) cudaFree(ctx->d_tc_masks);
   if (ctx->d_tc_flags) cudaFree(ctx->d_tc_flags);
+  if (ctx->d_tc_trace) cudaFree(ctx->d_tc_trace);
+  ctx->d_tc_trace = nullptr;
   ctx->d_tc_blob = nullptr;
   ctx->d_tc_bias = nullptr;
   ctx->d_tc_masks = nullptr;
@@ -1065,6 +1114,7 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.jac = d_jac;
   P.masks = reinterpret_cast<uint32_t*>(ctx->d_tc_masks);
   P.flags = ctx->d_tc_flags;
+  P.trace = ctx->d_tc_trace;
   P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
   const bool pair = hm_tc_pair_mode();
@@ -1127,6 +1177,24 @@ extern "C" int hm_debug_tc_wait_cycles(hm_context* ctx, unsigned long long* out)
   HM_CUDA(cudaDeviceSynchronize());
   HM_CUDA(cudaMemcpy(out, ctx->d_tc_flags + 8, sizeof(unsigned long long) * 13, cudaMemcpyDeviceToHost));
   HM_CUDA(cudaMemset(ctx->d_tc_flags + 8, 0, sizeof(unsigned long long) * 13));
+  return HM_OK;
+}
+
+// Debug export: with `enable` != 0 allocates (and clears) the timeline buffer so that the following decoder launches record
+// into it; with h_out != NULL copies 3 regions x 8192 (code, clock) pairs to the host.  enable == 0 frees the buffer.
+extern "C" int hm_debug_tc_trace(hm_context* ctx, int enable, uint32_t* h_out) {
+  HM_CHECK(ctx, "hm_debug_tc_trace: null context");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  HM_CUDA(cudaDeviceSynchronize());
+  const size_t bytes = sizeof(uint32_t) * 3 * 8192 * 2;
+  if (h_out && ctx->d_tc_trace) HM_CUDA(cudaMemcpy(h_out, ctx->d_tc_trace, bytes, cudaMemcpyDeviceToHost));
+  if (enable) {
+    if (!ctx->d_tc_trace) HM_CUDA(cudaMalloc(&ctx->d_tc_trace, bytes));
+    HM_CUDA(cudaMemset(ctx->d_tc_trace, 0, bytes));
+  } else if (ctx->d_tc_trace) {
+    cudaFree(ctx->d_tc_trace);
+    ctx->d_tc_trace = nullptr;
+  }
   return HM_OK;
 }
 
