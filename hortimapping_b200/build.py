@@ -29,7 +29,7 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    flags = [f for f in FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in FLAGS if f != "--use_fast_math=false"] + os.environ.get("HM_EXTRA_NVCC_FLAGS", "").split()
     cmd = [NVCC] + flags + ["-o", LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -37,11 +37,14 @@ constexpr int kAChunkBytes = 16384;                // 128 stacked rows (64 point
 constexpr int kSmemA = 0;
 constexpr int kSmemStages = 131072;
 constexpr int kSmemBars = kSmemStages + kWeightRing;             // 229376
-constexpr int kSmemTotal = kSmemBars + 256 + 512;
-constexpr int kEpiWarps = 8;
+constexpr int kSmemTotal = kSmemBars + 256 + 1024;
+constexpr int kEpiWarps = 16;
 constexpr int kCtrlWarps = 4;                      // one full warpgroup: producer, MMA issuer, two idle warps (setmaxnreg is per warpgroup)
 constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
-constexpr int kCtrlRegs = 64, kEpiRegs = 216;      // 128 x 64 + 256 x 216 = 63488 <= 65536 registers per SM
+// setmaxnreg moves registers inside the CTA's OWN allocation (threads x launch registers = 640 x 96): the control warpgroup
+// gives up 128 x (96 - 24) = 9216 registers and the 512 epilogue threads can take at most that many: 96 + 16 = 112.  (A request
+// the pool cannot satisfy does not fail, it spins forever -- measured.)
+constexpr int kCtrlRegs = 24, kEpiRegs = 112;
 constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per forward layer
 
 // barrier slots (8 bytes each) inside the barrier block
@@ -96,11 +99,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity);
+// HM_TC_COUNTERS (build flag) keeps per-role wait-cycle counters for hm_debug_tc_wait_cycles; off in the product build
 template <bool kCluster>
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+#ifdef HM_TC_COUNTERS
   long long t0 = clock64();
+#endif
   if constexpr (kCluster) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+#ifdef HM_TC_COUNTERS
   acc += clock64() - t0;
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -324,10 +332,8 @@ __device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int 
   *reinterpret_cast<__half2*>(base + sw128_offset(a_row(p, 1), k)) = ll;
 }
 
-// k-chunk order of an 8-chunk op.  Epilogue warp group h2 (0/1) owns output columns [128*h2, +128) of each
-// 256-column half and finishes them in four 64-column steps j: chunks {0,1,4,5} (h2 = 0) and {2,3,6,7} (h2 = 1).
-// The A operand therefore becomes ready two chunks per step -- {0,2}, {1,3}, {4,6}, {5,7} -- and that is the
-// order in which the MMA warp (and the weight blob) walk K.
+// k-chunk order of an 8-chunk op: k-step s multiplies chunks {0,2}, {1,3}, {4,6}, {5,7}.  Steps 0,1 read the chunks that the
+// previous op's output half 0 becomes (0..3), steps 2,3 those of its half 1 (4..7).
 __host__ __device__ __forceinline__ int chunk_of(int step, int which) { return (step & 1) + 4 * (step >> 1) + 2 * which; }
 
 // Accumulation groups of one op, in issue order.  A group = (k-step, 256-column output half nh).  For an 8-chunk op with
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
-  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][2 warp groups]
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][4 column groups]
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;                       // 0 = leader (MMA issuer) of the pair
   const uint32_t lead_bars = kPair ? mapa_rank(bars, 0) : bars;               // the leader's barrier block (cluster address)
@@ -503,96 +509,103 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    // ===================== epilogue warps (8) =====================
-    // Warp (sp, h2): TMEM sub-partition sp = warp % 4 holds the hi rows (lanes 0..15) and lo rows (lanes 16..31) of
-    // points 16*sp .. 16*sp+15; warp group h2 owns columns [128*h2, +128) of each 256-column output half.  With the
-    // 16x256b load shape thread t holds points pA = 16*sp + t/4 and pB = pA + 8, columns 8e + 2(t%4) + {0,1}:
-    // the hi-row and lo-row results of one (point, column) arrive in the SAME thread and are summed there.
+    // ===================== epilogue warps (16) =====================
+    // Warp (sp, h4): TMEM sub-partition sp = warp % 4 holds the hi rows (lanes 0..15) and lo rows (lanes 16..31) of
+    // points 16*sp .. 16*sp+15; column group h4 owns columns [64*h4, +64) of each 256-column output half, i.e. exactly
+    // k-chunk 4*nh + h4 of the next op's A operand.  With the 16x256b load shape thread t holds points pA = 16*sp + t/4
+    // and pB = pA + 8, columns 8e + 2(t%4) + {0,1}: the hi-row and lo-row results of one (point, column) arrive in the
+    // SAME thread and are summed there.  Four warps per scheduler keep the (latency-bound) conversion code busy.
     const int e_w = warp - kCtrlWarps;
     const int sp = warp & 3;
-    const int h2 = e_w >> 2;
+    const int h4 = e_w >> 2;
     const int tq = lane & 3;                 // column pair inside an 8-column block
     const int pA = 16 * sp + (lane >> 2), pB = pA + 8;
-    const uint32_t t_hi = tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * h2;
+    const uint32_t t_hi = tmem_base + ((uint32_t)(32 * sp) << 16) + 64 * h4;
     const uint32_t t_lo = t_hi + (16u << 16);
-    uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 4;   // [op][thread][4 words]
+    uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 2;   // [op][thread][2 words]
+    constexpr size_t kMaskStride = (size_t)kEpiWarps * 32 * 2;
     uint32_t op_seq = 0, gseq = 0;
     int sat = 0;
+#ifdef HM_TC_COUNTERS
     long long t_pfull = 0, t_pbody = 0, t_fin = 0;       // debug counters (hm_debug_tc_wait_cycles)
     const long long t_epi_begin = clock64();
-    auto publish = [&](int j) {              // this warp's 64-column chunk of step j is written
+#endif
+    auto publish = [&](int j) {              // this warp's part of k-step j of the next A operand is written
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_A_READY + j)); else mbar_arrive(bar(BAR_A_READY + j)); }
     };
-    // Column (within the 512-wide layer) of accumulator pair i = 32*nh + 8*cb + 2*e: 256*nh + 128*h2 + 32*cb + 8*e + 2*tq.
-    // Its A-operand address: chunk 4*nh + 2*h2 + (cb >> 1), 16-byte unit 4*(cb & 1) + e (XOR row & 7), byte 4*tq.
-    auto col_of = [&](int nh, int cb, int e) { return 256 * nh + 128 * h2 + 32 * cb + 8 * e + 2 * tq; };
+    // Column (within the 512-wide layer) of accumulator pair i = 8*nh + 4*cb + e: 256*nh + 64*h4 + 32*cb + 8*e + 2*tq.
+    // Its A-operand address: chunk 4*nh + h4, 16-byte unit 4*cb + e (XOR row & 7), byte 4*tq.
+    auto col_of = [&](int nh, int cb, int e) { return 256 * nh + 64 * h4 + 32 * cb + 8 * e + 2 * tq; };
     const uint32_t r7 = (uint32_t)(lane >> 2) & 7u;
-    uint8_t* const st_base = smem + kSmemA + (uint32_t)(2 * h2) * kAChunkBytes + 4 * tq;
-    const uint32_t rowA_hi = (uint32_t)(a_row(pA, 0) >> 3) * 1024 + (a_row(pA, 0) & 7) * 128;
-    const uint32_t rowA_lo = rowA_hi + 2048, rowB_hi = rowA_hi + 1024, rowB_lo = rowA_hi + 3072;   // +16 rows / +8 rows / +24 rows
+    uint8_t* const st_base = smem + kSmemA + (uint32_t)h4 * kAChunkBytes + 4 * tq +
+                             (uint32_t)(a_row(pA, 0) >> 3) * 1024 + (a_row(pA, 0) & 7) * 128;      // hi row of point A
     uint32_t sat2 = 0;
     auto store2 = [&](int nh, int cb, int e, float2 va, float2 vb) {
-      const uint32_t off = (uint32_t)(4 * nh + (cb >> 1)) * kAChunkBytes + (((uint32_t)(4 * (cb & 1) + e) ^ r7) << 4);
+      const uint32_t off = (uint32_t)(4 * nh) * kAChunkBytes + (((uint32_t)(4 * cb + e) ^ r7) << 4);
       uint32_t ha, la, hb, lb;
       split2(va, ha, la, sat2);
       split2(vb, hb, lb, sat2);
-      *reinterpret_cast<uint32_t*>(st_base + off + rowA_hi) = ha;
-      *reinterpret_cast<uint32_t*>(st_base + off + rowA_lo) = la;
-      *reinterpret_cast<uint32_t*>(st_base + off + rowB_hi) = hb;
-      *reinterpret_cast<uint32_t*>(st_base + off + rowB_lo) = lb;
+      *reinterpret_cast<uint32_t*>(st_base + off) = ha;                 // rows: A hi, +16 rows A lo, +8 rows B hi, +24 rows B lo
+      *reinterpret_cast<uint32_t*>(st_base + off + 2048) = la;
+      *reinterpret_cast<uint32_t*>(st_base + off + 1024) = hb;
+      *reinterpret_cast<uint32_t*>(st_base + off + 3072) = lb;
     };
     for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
       const int64_t tile = kPair ? 2 * unit + rank : unit;       // the odd CTA of the last pair may get an all-padding tile
       const int64_t growA = tile * HM_TC_TILE_M + pA, growB = tile * HM_TC_TILE_M + pB;
       const bool okA = growA < n_rows, okB = growB < n_rows;
+      // raw input x0 = [latent(32), xyz(3)] of the two points of this thread (deep_sdf_decoder.py:76-88); the pointers
+      // are rebuilt where they are needed (tile start, the skip-concat columns) instead of living in registers
       const int64_t lrA = okA ? growA : (n_rows - 1), lrB = okB ? growB : (n_rows - 1);
-      // raw input x0 = [latent(32), xyz(3)] of the two points of this thread (deep_sdf_decoder.py:76-88)
-      const float *latA, *xyzA, *latB, *xyzB;
-      if (P.rows) { latA = P.rows + lrA * HM_IN; xyzA = latA + HM_LATENT; latB = P.rows + lrB * HM_IN; xyzB = latB + HM_LATENT; }
-      else {
-        latA = P.latents + (size_t)(P.row_latent ? P.row_latent[lrA] : 0) * HM_LATENT; xyzA = P.xyz + lrA * 3;
-        latB = P.latents + (size_t)(P.row_latent ? P.row_latent[lrB] : 0) * HM_LATENT; xyzB = P.xyz + lrB * 3;
-      }
-      auto x0A = [&](int k) { return k < HM_LATENT ? latA[k] : (k < HM_IN ? xyzA[k - HM_LATENT] : 0.f); };
-      auto x0B = [&](int k) { return k < HM_LATENT ? latB[k] : (k < HM_IN ? xyzB[k - HM_LATENT] : 0.f); };
-      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); warp group h2 writes k in [32*h2, +32)
+      const int32_t liA = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lrA) : 0;      // latent-table row of each point
+      const int32_t liB = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lrB) : 0;
+      auto x0 = [&](int64_t lr, int32_t li, int k) -> float {
+        if (k >= HM_IN) return 0.f;
+        if (P.rows) return __ldg(P.rows + lr * HM_IN + k);
+        if (k < HM_LATENT) return __ldg(P.latents + (size_t)li * HM_LATENT + k);
+        return __ldg(P.xyz + lr * 3 + (k - HM_LATENT));
+      };
+      auto x0A = [&](int k) { return x0(lrA, liA, k); };
+      auto x0B = [&](int k) { return x0(lrB, liB, k); };
+      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group h4 writes k in [16*h4, +16)
       {
         const float s0 = P.plan.ops[0].in_scale;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 32 * h2 + 8 * e + 2 * tq;
+        for (int e = 0; e < 2; ++e) {
+          const int k = 16 * h4 + 8 * e + 2 * tq;
           store_pair(smem, 0, pA, k, x0A(k) * s0, x0A(k + 1) * s0, sat);
           store_pair(smem, 0, pB, k, x0B(k) * s0, x0B(k + 1) * s0, sat);
         }
         for (int j = 0; j < 4; ++j) publish(j);
       }
       float fA = 0.f, fB = 0.f;
-      // Accumulators of this thread, as column pairs: acc[16*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}.  They and
-      // the ReLU bits live across op boundaries: the last quarter of an op (output half 1, cb = 2,3) is finalized only after
-      // the first partial of the NEXT op has been collected (schedule below), so that neither TMEM buffer waits for it.
-      float2 accA[32], accB[32];
-      uint32_t m0A = 0u, m0B = 0u, m1A = 0u, m1B = 0u;   // ReLU bits (half 0 | half 1) x (point A | point B) of the current op
-      uint32_t pmA = 0u, pmB = 0u;                       // half-1 bits of the previous op, for its deferred quarter
+      // Accumulators of this thread, as column pairs: acc[8*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}.  They and
+      // the ReLU bits live across op boundaries: output half 1 of an op is finalized only after the first partial of the
+      // NEXT op has been collected (schedule below), so that the tensor core never waits for it.
+      float2 accA[16], accB[16];
+      uint32_t mA = 0u, mB = 0u;             // ReLU bits of the current op: bits 0..15 output half 0, bits 16..31 half 1
+      uint32_t pmA = 0u, pmB = 0u;           // ... of the previous op (for its deferred half 1)
       float dotA = 0.f, dotB = 0.f;
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
+      const std::integral_constant<int, 2> I2{};
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op, ++op_seq) {
         const hm_tc_op& o = P.plan.ops[op];
         const float unscale = o.out_unscale;
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
         const float k_mul = unscale * s_next;
-        const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, warp group 0 only
+        const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, column group 0 only
         const bool wide = (o.n_kchunks != 1);
-        const bool has_pending = (op != 0 && op != 8);   // the previous op left its last quarter to this one
+        const bool has_pending = (op != 0 && op != 8);   // the previous op left its output half 1 to this one
         const bool defer = (op != 7 && op != 15);        // ... and this op leaves its own to the next
-        pmA = m1A; pmB = m1B;
-        m0A = m0B = m1A = m1B = 0u;
+        pmA = mA; pmB = mB;
+        mA = mB = 0u;
         if (kJac && op >= 8 && op < 15) {
-          const uint4 mw = *reinterpret_cast<const uint4*>(my_masks + (size_t)(14 - op) * kEpiWarps * 32 * 4);   // ReLU mask of h_{l-1}, l = 15 - op
-          m0A = mw.x; m1A = mw.y; m0B = mw.z; m1B = mw.w;
+          const uint2 mw = *reinterpret_cast<const uint2*>(my_masks + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
+          mA = mw.x; mB = mw.y;
         }
         // collect the partial accumulator of one (step, n-half) group: hi-row and lo-row results meet in this thread.
         // FIRST: the group opens the op for this output half (overwrite instead of accumulate).
@@ -600,104 +613,113 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           constexpr int nh = decltype(NH)::value;
           constexpr bool first = decltype(FIRST)::value != 0;
           const uint32_t buf = gseq & 1;
+#ifdef HM_TC_COUNTERS
           const long long tp0 = clock64();
+#endif
           mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
+#ifdef HM_TC_COUNTERS
           const long long tp1 = clock64();
           t_pfull += tp1 - tp0;
+#endif
           tc_fence_after();
           if (e_w == 0 && lane == 0) trace(1 + rank, 10, op, gseq & 0xffff);
-          // four 32-column pieces (narrow B0: two, warp group 0 only); piece c+1 is in flight while piece c is added
+          // two 32-column pieces of this warp's 64 columns (narrow B0: column group 0 only)
           const uint32_t t_h = t_hi + buf * 256, t_l = t_lo + buf * 256;
-          auto load = [&](int c, float2 (&vh)[8], float2 (&vl)[8]) {
-            tmem_ld_16x256b_x4(t_h + 32 * c, reinterpret_cast<float*>(vh));
-            tmem_ld_16x256b_x4(t_l + 32 * c, reinterpret_cast<float*>(vl));
-          };
-          auto add = [&](int c, const float2 (&vh)[8], const float2 (&vl)[8]) {   // v[2q] = point A pair, v[2q+1] = point B pair
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = 16 * nh + 4 * c + q;
-              if constexpr (first) {
-                accA[i] = add2(vh[2 * q], vl[2 * q]);
-                accB[i] = add2(vh[2 * q + 1], vl[2 * q + 1]);
-              } else {
-                accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
-                accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
-              }
-            }
-          };
           auto release = [&]() {               // all TMEM reads of this buffer are complete
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_PART_EMPTY + buf)); else mbar_arrive(bar(BAR_PART_EMPTY + buf)); }
           };
-          if (narrow && h2 != 0) {
+          if (narrow && h4 != 0) {
             release();
           } else {
-            float2 vh0[8], vl0[8], vh1[8], vl1[8];
-            load(0, vh0, vl0);
-            tmem_ld_wait_dep(vh0, vl0);
-            load(1, vh1, vl1);
-            add(0, vh0, vl0);
-            tmem_ld_wait_dep(vh1, vl1);
-            if (narrow) {
-              release();
-              add(1, vh1, vl1);
-            } else {
-              load(2, vh0, vl0);
-              add(1, vh1, vl1);
-              tmem_ld_wait_dep(vh0, vl0);
-              load(3, vh1, vl1);
-              add(2, vh0, vl0);
-              tmem_ld_wait_dep(vh1, vl1);
-              release();
-              add(3, vh1, vl1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float2 vh[8], vl[8];
+              tmem_ld_16x256b_x4(t_h + 32 * c, reinterpret_cast<float*>(vh));
+              tmem_ld_16x256b_x4(t_l + 32 * c, reinterpret_cast<float*>(vl));
+              tmem_ld_wait_dep(vh, vl);
+              if (c == 1) release();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {        // v[2q] = point A pair, v[2q+1] = point B pair
+                const int i = 8 * nh + 4 * c + q;
+                if constexpr (first) {
+                  accA[i] = add2(vh[2 * q], vl[2 * q]);
+                  accB[i] = add2(vh[2 * q + 1], vl[2 * q + 1]);
+                } else {
+                  accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
+                  accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
+                }
+              }
             }
           }
           ++gseq;
+#ifdef HM_TC_COUNTERS
           t_pbody += clock64() - tp1;
+#endif
           if (e_w == 0 && lane == 0) trace(1 + rank, 12, op, gseq & 0xffff);
         };
-        // Turn one finished quarter (output half nh, column blocks cb = 2*jj, 2*jj+1) of op `opx` into the next op's A operand
-        // (k-step 2*nh + jj) or the final outputs.  kClass: 0 = any op, 1 = opx is a hidden layer (forward or backward, the
-        // deferred quarter), 2 = opx is lin7.
-        auto fin_piece = [&](auto NH, auto JJ, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x,
-                             uint32_t& mA_, uint32_t& mB_) {
-          constexpr int nh = decltype(NH)::value, jj = decltype(JJ)::value, kClass = decltype(CLASS)::value;
+        // Turn the finished output half nh of op `opx` into the next op's A chunk 4*nh + h4 (k-steps 2*nh, 2*nh+1) or the
+        // final outputs.  kClass: 0 = any op, 1 = opx is a hidden layer (forward or backward: the deferred half), 2 = lin7.
+        auto finalize = [&](auto NH, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x,
+                            uint32_t& mA_, uint32_t& mB_) {
+          constexpr int nh = decltype(NH)::value, kClass = decltype(CLASS)::value;
+#ifdef HM_TC_COUNTERS
           const long long tf0 = clock64();
-          if (e_w == 0 && lane == 0) trace(1 + rank, 13, opx, 2 * nh + jj);
+#endif
+          if (e_w == 0 && lane == 0) trace(1 + rank, 13, opx, nh);
           if (kClass != 2 && opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
             const float* bias = P.bias + opx * HM_HIDDEN;
             const float2 kk = make_float2(k_mul_x, k_mul_x);
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int cb = 2 * jj + cc;
+            for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
+                const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
                 const int col = col_of(nh, cb, e);
                 const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
                 float2 ya = fma2(accA[i], kk, bz), yb = fma2(accB[i], kk, bz);
                 mA_ |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
                 mB_ |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
                 ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                if (nh == 1 && jj == 1 && opx == 3 && col + 1 >= HM_SKIP_COL) {
-                  // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat)
-                  if (col >= HM_SKIP_COL) { ya.x = x0A(col - HM_SKIP_COL) * s_next_x; yb.x = x0B(col - HM_SKIP_COL) * s_next_x; mA_ &= ~(1u << bit); mB_ &= ~(1u << bit); }
-                  ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next_x; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next_x;
-                  mA_ &= ~(1u << (bit + 1)); mB_ &= ~(1u << (bit + 1));
-                }
                 store2(nh, cb, e, ya, yb);
               }
             }
-            publish(2 * nh + jj);
+            if (nh == 1 && opx == 3 && h4 == 3) {
+              // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat, deep_sdf_decoder.py:87-88).
+              // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the last
+              // column group rewrites its elements from column 476 on and clears their ReLU bits.
+#pragma unroll
+              for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                for (int e = (cb == 0 ? 3 : 0); e < 4; ++e) {
+                  const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
+                  const int col = col_of(nh, cb, e);
+                  if (col + 1 >= HM_SKIP_COL) {
+                    float2 ya, yb;
+                    if (col >= HM_SKIP_COL) {
+                      ya.x = x0A(col - HM_SKIP_COL) * s_next_x; yb.x = x0B(col - HM_SKIP_COL) * s_next_x;
+                      mA_ &= ~(1u << bit); mB_ &= ~(1u << bit);
+                    } else {                        // column 476: the last real lin3 output
+                      const float bz = __ldg(bias + col);
+                      ya.x = fmaxf(fmaf(accA[i].x, k_mul_x, bz), 0.f); yb.x = fmaxf(fmaf(accB[i].x, k_mul_x, bz), 0.f);
+                    }
+                    ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next_x; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next_x;
+                    mA_ &= ~(1u << (bit + 1)); mB_ &= ~(1u << (bit + 1));
+                    store2(nh, cb, e, ya, yb);
+                  }
+                }
+              }
+            }
+            publish(2 * nh); publish(2 * nh + 1);
           } else if (kClass != 1 && opx == 7) {
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
             const float* bias = P.bias + 7 * HM_HIDDEN;
             const float2 uu = make_float2(unscale_x, unscale_x);
 #pragma unroll
-            for (int ii = 8 * jj; ii < 8 * jj + 8; ++ii) {
-              const int i = 16 * nh + ii, bit = 2 * ii;
+            for (int ii = 0; ii < 8; ++ii) {
+              const int i = 8 * nh + ii, bit = 16 * nh + 2 * ii;
               const int col = col_of(nh, ii >> 2, ii & 3);
               const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
               const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col));
@@ -710,47 +732,54 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           } else if (kClass != 2 && opx > 7 && opx < 15) {
             // ---------------- backward through lin_l (l = 15 - opx = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int cb = 2 * jj + cc;
+            for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int i = 16 * nh + 4 * cb + e, bit = 8 * cb + 2 * e;
-                if (nh == 1 && jj == 1 && opx == 11) {
-                  const int col = col_of(nh, cb, e);
-                  if (col + 1 >= HM_SKIP_COL) {
-                    // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0
-                    // (deep_sdf_decoder.py:87-88).  They are parked in the output Jacobian row; B0 adds the rest.
-                    if (col >= HM_SKIP_COL) {
-                      if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale_x);
-                      if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale_x);
-                    }
-                    if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale_x);
-                    if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale_x);
-                  }
-                }
+                const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
                 const float2 sa = make_float2(((mA_ >> bit) & 1u) ? k_mul_x : 0.f, ((mA_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
                 const float2 sb = make_float2(((mB_ >> bit) & 1u) ? k_mul_x : 0.f, ((mB_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
                 store2(nh, cb, e, make_float2(accA[i].x * sa.x, accA[i].y * sa.y), make_float2(accB[i].x * sb.x, accB[i].y * sb.y));
               }
             }
-            if (nh == 1 && jj == 1 && opx == 11) __threadfence_block();
-            publish(2 * nh + jj);
+            if (nh == 1 && opx == 11 && h4 == 3) {
+              // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0 (deep_sdf_decoder.py:87-88).
+              // They are parked in the output Jacobian row; B0 adds the rest.  (Their ReLU bits are clear, so the loop above wrote
+              // zeros for them into the next A operand.)
+#pragma unroll
+              for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                for (int e = (cb == 0 ? 3 : 0); e < 4; ++e) {
+                  const int i = 8 * nh + 4 * cb + e;
+                  const int col = col_of(nh, cb, e);
+                  if (col >= HM_SKIP_COL) {
+                    if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale_x);
+                    if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale_x);
+                  }
+                  if (col + 1 >= HM_SKIP_COL) {
+                    if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale_x);
+                    if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale_x);
+                  }
+                }
+              }
+              __threadfence_block();
+            }
+            publish(2 * nh); publish(2 * nh + 1);
           }
+#ifdef HM_TC_COUNTERS
           t_fin += clock64() - tf0;
-          if (e_w == 0 && lane == 0) trace(1 + rank, 14, opx, 2 * nh + jj);
+#endif
+          if (e_w == 0 && lane == 0) trace(1 + rank, 14, opx, nh);
         };
-        // ---- Schedule of one op (groups in the issue order of group_of(); P = promote, F(nh, jj) = finalize a quarter):
-        //        P(0,0) [F'(1,1) of the previous op] P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0,0) P(2,1) F(0,1) P(3,1) F(1,0)
-        //      Output half 0 is complete two groups before the op ends; finalizing is cut into quarters that alternate
-        //      with the promotions, so a TMEM buffer is never held for longer than one quarter and the tensor core runs on.
+        // ---- Schedule of one op (groups in the issue order of group_of(); P = promote, F(nh) = finalize an output half):
+        //        P(0,0) [F'(1) of the previous op] P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0) P(2,1) P(3,1)   [F(1) -> next op]
+        //      Output half 0 is complete two groups before the op ends and is turned into the next op's A chunks 0..3 while
+        //      the tensor core still works on half 1; half 1 is finalized under the next op's first groups (which read
+        //      chunks 0..3 only).
         promote(I0, I1);
         if (has_pending) {
           const float q_unscale = P.plan.ops[op - 1].out_unscale;
-          fin_piece(I1, I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pmA, pmB);
-          if (kJac && op - 1 < 7) {
-            uint32_t* mw = my_masks + (size_t)(op - 1) * kEpiWarps * 32 * 4;
-            mw[1] = pmA; mw[3] = pmB;
-          }
+          finalize(I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pmA, pmB);
+          if (kJac && op - 1 < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)(op - 1) * kMaskStride) = make_uint2(pmA, pmB);
         }
         if (narrow) {
 #pragma unroll 1
@@ -761,29 +790,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           } else {
             promote(I1, I1);       // F0: both output halves read A chunk 0 -- collect both before it is overwritten
           }
-          fin_piece(I0, I0, I0, op, k_mul, unscale, s_next, m0A, m0B);
-          if (wide) promote(I1, I0);
-          fin_piece(I0, I1, I0, op, k_mul, unscale, s_next, m0A, m0B);
-          if (wide) promote(I1, I0);
-          fin_piece(I1, I0, I0, op, k_mul, unscale, s_next, m1A, m1B);
-          if (!defer) fin_piece(I1, I1, std::integral_constant<int, 2>{}, op, k_mul, unscale, s_next, m1A, m1B);
+          finalize(I0, I0, op, k_mul, unscale, s_next, mA, mB);
+          if (wide) { promote(I1, I0); promote(I1, I0); }
+          if (!defer) finalize(I1, I2, op, k_mul, unscale, s_next, mA, mB);
         }
-        if (op < 7) {
-          if (kJac) {              // half-0 words now, half-1 words after the deferred quarter
-            uint32_t* mw = my_masks + (size_t)op * kEpiWarps * 32 * 4;
-            mw[0] = m0A; mw[2] = m0B;
-          }
-        } else if (op == 7) {
+        if (op == 7) {
           dotA += __shfl_xor_sync(0xffffffffu, dotA, 1); dotA += __shfl_xor_sync(0xffffffffu, dotA, 2);
           dotB += __shfl_xor_sync(0xffffffffu, dotB, 1); dotB += __shfl_xor_sync(0xffffffffu, dotB, 2);
-          if (tq == 0) { dot_scratch[pA * 2 + h2] = dotA; dot_scratch[pB * 2 + h2] = dotB; }
+          if (tq == 0) { dot_scratch[pA * 4 + h4] = dotA; dot_scratch[pB * 4 + h4] = dotB; }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           const float b8 = __ldg(P.b8);
-          fA = tanhf(dot_scratch[pA * 2] + dot_scratch[pA * 2 + 1] + b8);
-          fB = tanhf(dot_scratch[pB * 2] + dot_scratch[pB * 2 + 1] + b8);
+          const float4 dA = *reinterpret_cast<const float4*>(dot_scratch + pA * 4), dB = *reinterpret_cast<const float4*>(dot_scratch + pB * 4);
+          fA = tanhf(((dA.x + dA.y) + (dA.z + dA.w)) + b8);
+          fB = tanhf(((dB.x + dB.y) + (dB.z + dB.w)) + b8);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           dotA = dotB = 0.f;
-          if (h2 == 0 && tq == 0) {
+          if (h4 == 0 && tq == 0) {
             if (okA) P.sdf[growA] = fA;
             if (okB) P.sdf[growB] = fB;
           }
@@ -791,26 +813,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             // d7 = (1 - f^2) * w8 * relu'(h7): A operand of B7
             const float cA = (1.f - fA * fA) * s_next, cB = (1.f - fB * fB) * s_next;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int nh = j >> 1;
-              const uint32_t mA_ = nh ? m1A : m0A, mB_ = nh ? m1B : m0B;
+            for (int nh = 0; nh < 2; ++nh) {
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const int cb = 2 * (j & 1) + cc;
+              for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const int bit = (8 * cb + 2 * e);
+                  const int bit = 16 * nh + 8 * cb + 2 * e;
                   const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col_of(nh, cb, e)));
-                  store2(nh, cb, e, make_float2(((mA_ >> bit) & 1u) ? cA * wz.x : 0.f, ((mA_ >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
-                         make_float2(((mB_ >> bit) & 1u) ? cB * wz.x : 0.f, ((mB_ >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
+                  store2(nh, cb, e, make_float2(((mA >> bit) & 1u) ? cA * wz.x : 0.f, ((mA >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
+                         make_float2(((mB >> bit) & 1u) ? cB * wz.x : 0.f, ((mB >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
                 }
               }
-              publish(j);
+              publish(2 * nh); publish(2 * nh + 1);
             }
           }
         } else if (op == 15) {
-          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all owned by warp group 0) + the parked skip gradient
-          if (h2 == 0) {
+          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all owned by column group 0) + the parked skip gradient
+          if (h4 == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {              // nh = 0, cb = 0,1: columns 32*cb + 8*e + 2*tq + {0,1} < 64
               const int col = 32 * (i >> 2) + 8 * (i & 3) + 2 * tq;
@@ -828,12 +847,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       }
     }
     if (sat | (int)((sat2 & 0xffffu) >= 0x7bffu) | (int)((sat2 >> 16) >= 0x7bffu)) atomicAdd(P.flags, 1);
+#ifdef HM_TC_COUNTERS
     if (P.flags && e_w == 0 && lane == 0) {
       atomicAdd((unsigned long long*)(P.flags + 18 + 8 * rank), (unsigned long long)t_pfull);
       atomicAdd((unsigned long long*)(P.flags + 20 + 8 * rank), (unsigned long long)t_pbody);
       atomicAdd((unsigned long long*)(P.flags + 22 + 8 * rank), (unsigned long long)t_fin);
       atomicAdd((unsigned long long*)(P.flags + 24 + 8 * rank), (unsigned long long)(clock64() - t_epi_begin));
     }
+#endif
   }
   tc_fence_before();
   __syncthreads();

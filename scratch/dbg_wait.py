@@ -17,6 +17,8 @@ for jac in [True, False]:
     e0.record(); dec._eval_rows(t, with_jac=jac); e1.record(); torch.cuda.synchronize()
     L.hm_debug_tc_wait_cycles(dec.handle, out)
     v=[int(x) for x in out]; tot=v[4]
+    if tot == 0:
+        print('jac',jac,'ms',e0.elapsed_time(e1),'(library built without -DHM_TC_COUNTERS)'); continue
     nlead = 148 if os.environ.get('HM_TC_PAIR')=='0' else 74
     for nm,o in (('leader',5),('peer',9)):
         if v[o+3]: print('   epilogue[%s]: total %.0f  wait_full %.1f%%  promote %.1f%%  finalize %.1f%%'%(nm, v[o+3]/nlead, 100*v[o]/v[o+3], 100*v[o+1]/v[o+3], 100*v[o+2]/v[o+3]))

@@ -68,3 +68,62 @@ for name, order, fn in (('old', ORD_A, seq_old), ('S2 (current)', ORD_A, seq_s2)
     for (p, f) in ((700, 2000), (700, 2400), (500, 1500), (350, 1200)):
         P, F = p, f
         print('%-14s P=%4d F=%4d  time / MMA floor = %.3f' % (name, p, f, run(order, fn)))
+
+# ---- 16 epilogue warps: finalize works on whole output halves (publishes both k-steps of the half at its end)
+def seq16_nodefer(op):
+    return [('P', k) for k in range(6)] + [('F2', op, 0), ('P', 6), ('P', 7), ('F2', op, 1)]
+
+def seq16_defer(op):
+    return [('P', 0)] + ([('F2', op - 1, 1)] if op else []) + [('P', k) for k in range(1, 6)] + [('F2', op, 0), ('P', 6), ('P', 7)]
+
+def run16(order, fn, f0, f1):
+    global F
+    def expand(op):
+        out = []
+        for a in fn(op):
+            if a[0] == 'F2':
+                out.append(('F', a[1], a[2], 0, f1 if a[2] else f0))
+            else:
+                out.append(a)
+        return out
+    # re-implement with per-action finalize time; a half publishes steps 2nh and 2nh+1 together
+    a_ready = {(0, s): 0 for s in range(4)}
+    exec_end, promoted = {}, {}
+    t_mma = t_epi = 0
+    acts = [(op, a) for op in range(NOPS) for a in expand(op)]
+    gl = [(op, k) for op in range(NOPS) for k in range(8)]
+    gi = ai = 0
+    while gi < len(gl) or ai < len(acts):
+        progress = False
+        if gi < len(gl):
+            op, k = gl[gi]
+            step, nh = order[k]
+            need = [a_ready.get((op, step))] + ([promoted.get(gl[gi - 2])] if gi >= 2 else [])
+            if all(n is not None for n in need):
+                start = max([t_mma] + need)
+                exec_end[(op, k)] = t_mma = start + G
+                gi += 1
+                progress = True
+        if ai < len(acts):
+            op, a = acts[ai]
+            if a[0] == 'P':
+                e = exec_end.get((op, a[1]))
+                if e is not None:
+                    t_epi = max(t_epi, e + LAT) + P
+                    promoted[(op, a[1])] = t_epi + LAT
+                    ai += 1
+                    progress = True
+            else:
+                _, opx, nh, _, dur = a
+                t_epi += dur
+                a_ready[(opx + 1, 2 * nh)] = a_ready[(opx + 1, 2 * nh + 1)] = t_epi + LAT
+                ai += 1
+                progress = True
+        assert progress
+    return t_mma / (NOPS * 8 * G)
+
+print()
+for p in (600,):
+    P = p
+    for f0, f1 in ((2400, 3800), (2400, 2400), (1850, 2900), (1850, 1850), (1500, 1500)):
+        print('16 warps P=%d F0=%d F1=%d: no-defer %.3f   defer %.3f' % (p, f0, f1, run16(ORD_A, seq16_nodefer, f0, f1), run16(ORD_A, seq16_defer, f0, f1)))

@@ -23,4 +23,4 @@ for r in range(3):
 sel = sorted(e for e in ev if e[0] == unit and e[4] in ops)
 t0 = sel[0][1]
 for u, t, r, code, op, idx in sel:
-    print('%8d  %s  %-20s op %2d  %s' % (t - t0, ['MMA   ', '  EPI0', '  EPI1'][r], names.get(code, code), op, ('g%d' % idx) if r == 0 else (('q%d' % idx) if code >= 13 else ('seq%d' % idx))))
+    print('%8d  %s  %-20s op %2d  %s' % (t - t0, ['MMA   ', '  EPI0', '  EPI1'][r], names.get(code, code), op, ('g%d' % idx) if r == 0 else (("h%d" % idx) if code >= 13 else ('seq%d' % idx))))
