@@ -127,6 +127,8 @@ extern "C" void hm_destroy(hm_context* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->pinned) cudaFree(ctx->pinned);
+  if (ctx->mesh_ws) cudaFree(ctx->mesh_ws);
+  if (ctx->mesh_out) cudaFree(ctx->mesh_out);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->d_last_H) cudaFree(ctx->d_last_H);
@@ -242,15 +244,7 @@ extern "C" int hm_sdf_jacobian_rows(hm_context* ctx, const float* d_rows, int64_
 __global__ void voxel_grid_kernel(int n, float voxel_size, float cube_radius, int64_t total, float* __restrict__ xyz) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  float fn = (float)n;
-  float v2 = (float)(i % n);
-  float q1 = __fdiv_rn((float)i, fn);
-  float v1 = fmodf(q1, fn);
-  float q2 = __fdiv_rn(q1, fn);
-  float v0 = fmodf(q2, fn);
-  xyz[i * 3 + 0] = __fmul_rn(__fadd_rn(__fmul_rn(v0, voxel_size), -1.f), cube_radius);
-  xyz[i * 3 + 1] = __fmul_rn(__fadd_rn(__fmul_rn(v1, voxel_size), -1.f), cube_radius);
-  xyz[i * 3 + 2] = __fmul_rn(__fadd_rn(__fmul_rn(v2, voxel_size), -1.f), cube_radius);
+  for (int c = 0; c < 3; ++c) xyz[i * 3 + c] = hm_grid_coord(i, c, n, voxel_size, cube_radius);
 }
 
 extern "C" int hm_voxel_grid(hm_context* ctx, int32_t vol_dim, float cube_radius, float* d_xyz, void* stream) {
@@ -268,11 +262,18 @@ extern "C" int hm_sdf_grid(hm_context* ctx, const float* d_latent, int32_t vol_d
   HM_CHECK(ctx && d_latent && d_sdf && vol_dim >= 2 && vol_dim <= 1024, "hm_sdf_grid: bad argument");
   HM_CUDA(cudaSetDevice(ctx->device));
   int64_t total = (int64_t)vol_dim * vol_dim * vol_dim;
-  int rc = hm_ws2_reserve(ctx, sizeof(float) * 3 * total);
-  if (rc) return rc;
-  float* d_xyz = (float*)ctx->ws2;
-  rc = hm_voxel_grid(ctx, vol_dim, cube_radius, d_xyz, stream);
-  if (rc) return rc;
-  hm_rows rows = {nullptr, d_xyz, d_latent, nullptr, total, nullptr};
+  hm_rows rows = {nullptr, nullptr, d_latent, nullptr, total, nullptr};
+  rows.grid_n = vol_dim;
+  rows.grid_voxel = (float)(2.0 / (vol_dim - 1));
+  rows.grid_radius = cube_radius;
+  if (ctx->engine == HM_ENGINE_SIMT) {          // the validation engine reads explicit points
+    int rc = hm_ws2_reserve(ctx, sizeof(float) * 3 * total);
+    if (rc) return rc;
+    rc = hm_voxel_grid(ctx, vol_dim, cube_radius, (float*)ctx->ws2, stream);
+    if (rc) return rc;
+    rows.d_xyz = (const float*)ctx->ws2;
+    rows.grid_n = 0;
+  }
+  // tensor-core engine: the grid points are generated inside the decoder kernel (fused grid sample + decode)
   return hm_decode(ctx, rows, d_sdf, nullptr, (cudaStream_t)stream);
 }

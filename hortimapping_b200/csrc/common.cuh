@@ -84,6 +84,11 @@ struct hm_context {
   size_t ws_bytes = 0;
   void* ws2 = nullptr;             // optimiser workspace (separate so decoder calls never alias it)
   size_t ws2_bytes = 0;
+  void* mesh_ws = nullptr;         // iso-surface scratch (edge flags / scans) and outputs of the last hm_isosurface call
+  size_t mesh_ws_bytes = 0;
+  void* mesh_out = nullptr;
+  size_t mesh_out_bytes = 0;
+  int64_t mesh_n_verts = 0, mesh_n_faces = 0;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   hm_counters counters = {};
@@ -111,7 +116,25 @@ struct hm_rows {
   const int32_t* d_row_latent;  // [n] or NULL
   int64_t n;
   const int32_t* d_n_dynamic;   // optional device-side row count (<= n); NULL = use n
+  // fused mesher grid (wild_completion/utils.py:542-562): when grid_n > 0 the xyz of row i is create_voxel_grid(grid_n)[i] *
+  // grid_radius, generated inside the decoder kernel (d_xyz is ignored; all rows use latent 0)
+  int32_t grid_n = 0;
+  float grid_voxel = 0.f;
+  float grid_radius = 0.f;
 };
+
+// one coordinate (c = 0,1,2) of point i of the reference's voxel grid, in the reference's fp32 operation order (the grid is
+// "sheared": LongTensor / int is true division): idx -> float32, / n, fmod n, * voxel_size, + (-1), * cube_radius
+__device__ __forceinline__ float hm_grid_coord(int64_t i, int c, int n, float voxel_size, float cube_radius) {
+  const float fn = (float)n;
+  float v;
+  if (c == 2) v = (float)(i % n);
+  else {
+    const float q1 = __fdiv_rn((float)i, fn);
+    v = (c == 1) ? fmodf(q1, fn) : fmodf(__fdiv_rn(q1, fn), fn);
+  }
+  return __fmul_rn(__fadd_rn(__fmul_rn(v, voxel_size), -1.f), cube_radius);
+}
 
 int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st,
                    float* h_absmax_out /* [16] or NULL: calibration */);

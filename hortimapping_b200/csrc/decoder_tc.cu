@@ -71,6 +71,8 @@ struct TcParams {
   uint32_t* masks;            // [grid][8][64][16]
   int32_t* flags;             // [0] = saturation count
   uint32_t* trace;            // debug timeline of CTA 0 / 1 (hm_debug_tc_trace) or null
+  int32_t grid_n;             // > 0: xyz of row i = voxel grid point i (fused mesher grid, hm_rows)
+  float grid_voxel, grid_radius;
   float b0_in_scale_dummy;
 };
 
@@ -565,6 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         if (k >= HM_IN) return 0.f;
         if (P.rows) return __ldg(P.rows + lr * HM_IN + k);
         if (k < HM_LATENT) return __ldg(P.latents + (size_t)li * HM_LATENT + k);
+        if (P.grid_n > 0) return hm_grid_coord(lr, k - HM_LATENT, P.grid_n, P.grid_voxel, P.grid_radius);
         return __ldg(P.xyz + lr * 3 + (k - HM_LATENT));
       };
       auto x0A = [&](int k) { return x0(lrA, liA, k); };
@@ -1136,6 +1139,9 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.masks = reinterpret_cast<uint32_t*>(ctx->d_tc_masks);
   P.flags = ctx->d_tc_flags;
   P.trace = ctx->d_tc_trace;
+  P.grid_n = rows.grid_n;
+  P.grid_voxel = rows.grid_voxel;
+  P.grid_radius = rows.grid_radius;
   P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
   const bool pair = hm_tc_pair_mode();

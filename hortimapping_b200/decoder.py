@@ -170,6 +170,22 @@ class Decoder:
         check(self._L.hm_sdf_grid(self._h, lat.data_ptr(), vol_dim, float(cube_radius), out.data_ptr(), _stream_ptr(self.device)), "hm_sdf_grid")
         return out.view(vol_dim, vol_dim, vol_dim)
 
+    def isosurface(self, sdf_3d: torch.Tensor, level: float = 0.0, spacing: float = 1.0, affine_radius: Optional[float] = None):
+        """Zero level set of an (N,N,N) SDF grid on the device (hm_isosurface: marching tetrahedra, the device twin of
+        marching.marching_tetrahedra) -> vertices (V,3) float32, faces (F,3) int32 as CUDA tensors.  With `affine_radius`
+        the vertices are mapped to (v - 1) * radius as wild_completion/utils.py:583-585 does."""
+        vol = _f32c(sdf_3d, self.device)
+        n = int(vol.shape[0])
+        assert tuple(vol.shape) == (n, n, n), "isosurface expects a cubic (N,N,N) grid"
+        nv, nf = C.c_int64(0), C.c_int64(0)
+        st = _stream_ptr(self.device)
+        check(self._L.hm_isosurface(self._h, vol.data_ptr(), n, float(level), float(spacing), C.byref(nv), C.byref(nf), st), "hm_isosurface")
+        verts = torch.empty(nv.value, 3, device=self.device, dtype=torch.float32)
+        faces = torch.empty(nf.value, 3, device=self.device, dtype=torch.int32)
+        check(self._L.hm_isosurface_fetch(self._h, verts.data_ptr() if nv.value else None, faces.data_ptr() if nf.value else None,
+                                          0 if affine_radius is None else 1, float(affine_radius or 0.0), st), "hm_isosurface_fetch")
+        return verts, faces
+
     def voxel_grid(self, vol_dim: int, cube_radius: float = 1.0) -> torch.Tensor:
         out = torch.empty(vol_dim ** 3, 3, device=self.device, dtype=torch.float32)
         check(self._L.hm_voxel_grid(self._h, vol_dim, float(cube_radius), out.data_ptr(), _stream_ptr(self.device)), "hm_voxel_grid")

@@ -36,12 +36,26 @@ def convert_sdf_voxels_to_mesh(sdf_3d: torch.Tensor, cube_radius: float):
     return verts, faces
 
 
+def _skimage_available() -> bool:
+    try:
+        from skimage import measure  # type: ignore  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
 class MeshExtractor(object):
-    def __init__(self, decoder: Decoder, code_len=64, voxels_dim=64, cube_radius=1.0):
+    """`iso` selects the iso-surface extractor: "device" = hm_isosurface (marching tetrahedra on the GPU, only vertices and
+    faces leave the device), "skimage" = the reference's own host call, "auto" (default) = skimage when it is importable
+    (the mesh is then exactly what the reference builds from the same grid), else the device extractor."""
+
+    def __init__(self, decoder: Decoder, code_len=64, voxels_dim=64, cube_radius=1.0, iso: str = "auto"):
         self.decoder = decoder
         self.code_len = code_len
         self.voxels_dim = voxels_dim
         self.cube_radius = cube_radius
+        assert iso in ("auto", "device", "skimage")
+        self.iso = ("skimage" if _skimage_available() else "device") if iso == "auto" else iso
         with torch.no_grad():
             self.voxel_points = decoder.voxel_grid(self.voxels_dim, self.cube_radius)   # mesher.py:12
 
@@ -51,6 +65,9 @@ class MeshExtractor(object):
     def extract_mesh_from_code(self, code):
         """mesher.py:14-24."""
         sdf = self.sdf_grid(code)
+        if self.iso == "device":
+            v, f = self.decoder.isosurface(sdf, 0.0, 2.0 / (self.voxels_dim - 1), affine_radius=self.cube_radius)
+            return ForceKeyErrorDict(vertices=v.cpu().numpy(), faces=f.cpu().numpy())
         vertices, faces = convert_sdf_voxels_to_mesh(sdf.view(self.voxels_dim, self.voxels_dim, self.voxels_dim), self.cube_radius)
         return ForceKeyErrorDict(vertices=vertices.astype("float32"), faces=np.asarray(faces).astype("int32"))
 

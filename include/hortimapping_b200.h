@@ -150,6 +150,15 @@ int hm_voxel_grid(hm_context* ctx, int32_t vol_dim, float cube_radius, float* d_
 /* wild_completion/mesher.py:12-18: SDF of `latent` on that grid -> sdf[vol_dim^3] (C order). */
 int hm_sdf_grid(hm_context* ctx, const float* d_latent, int32_t vol_dim, float cube_radius, float* d_sdf, void* stream);
 
+/* wild_completion/utils.py:565-588 convert_sdf_voxels_to_mesh, on the device: zero level set of d_sdf [n][n][n] (C order) by
+ * marching tetrahedra (the reference calls skimage.measure.marching_cubes on the host; mesh parity is pinned at Chamfer
+ * level).  The mesh stays in the context; the counts come back on the host (synchronises the stream). */
+int hm_isosurface(hm_context* ctx, const float* d_sdf, int32_t n, double level, double spacing, int64_t* h_n_verts,
+                  int64_t* h_n_faces, void* stream);
+/* Copies that mesh to d_verts [n_verts][3] fp32 and d_faces [n_faces][3] int32; apply_affine != 0 maps the vertices to
+ * (v - 1) * cube_radius as utils.py:583-585 does. */
+int hm_isosurface_fetch(hm_context* ctx, float* d_verts, int32_t* d_faces, int32_t apply_affine, double cube_radius, void* stream);
+
 /* wild_completion/loss.py:219-243 compute_sdf_loss: res[n], J_pose[n][pose_dim], J_code[n][32]. */
 int hm_sdf_loss(hm_context* ctx, const float* d_latent, const float* d_pts_obj, int64_t n, int32_t scale_on,
                 float* d_res, float* d_J_pose, float* d_J_code, void* stream);

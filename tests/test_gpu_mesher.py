@@ -1,0 +1,84 @@
+"""GPU parity of the device iso-surface extractor (hm_isosurface) against the host extractor
+hortimapping_b200/marching.py, which it mirrors index by index: faces are compared exactly (integer work), vertices to
+fp32 rounding (both interpolate in fp64; the host keeps the first of several equivalent evaluations of a welded vertex)."""
+import numpy as np
+import pytest
+import torch
+
+from hortimapping_b200.marching import marching_tetrahedra
+from tests.helpers import load_npz
+
+pytestmark = pytest.mark.gpu
+
+
+def _sphere(n, r=0.6, c=(0.05, -0.1, 0.02)):
+    g = np.linspace(-1, 1, n, dtype=np.float32)
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    return (np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) - r).astype(np.float32)
+
+
+def _compare(dec, vol, level=0.0, spacing=1.0):
+    v_ref, f_ref = marching_tetrahedra(vol, level, (spacing,) * 3)
+    v, f = dec.isosurface(torch.from_numpy(vol).cuda(), level, spacing)
+    v, f = v.cpu().numpy(), f.cpu().numpy()
+    assert v.shape == v_ref.shape and f.shape == f_ref.shape, (v.shape, v_ref.shape, f.shape, f_ref.shape)
+    np.testing.assert_array_equal(f, f_ref)
+    if v.size:
+        scale = max(1.0, float(np.abs(v_ref).max()))
+        assert np.abs(v - v_ref).max() <= 2 * np.finfo(np.float32).eps * scale
+        assert (v != v_ref).any(axis=1).mean() <= 0.01          # all but a handful are bit-identical
+    return v, f
+
+
+def test_isosurface_matches_host_extractor_on_analytic_fields():
+    from tests.gpu_helpers import pepper_decoder
+    dec = pepper_decoder()
+    for n in (2, 3, 9, 20, 33):
+        _compare(dec, _sphere(n), 0.0, 2.0 / (n - 1))
+    g = np.random.default_rng(3)
+    noise = g.standard_normal((17, 17, 17)).astype(np.float32)      # every tetrahedron case, many surface sheets
+    _compare(dec, noise, 0.0, 1.0)
+    _compare(dec, noise, 0.25, 0.5)
+    flat = _sphere(12)
+    flat[flat > 0.3] = 0.0                                           # exact zeros on the outside (t = 0 / 1 interpolation)
+    _compare(dec, flat, 0.0, 1.0)
+
+
+def test_isosurface_empty_and_orientation():
+    from tests.gpu_helpers import pepper_decoder
+    dec = pepper_decoder()
+    v, f = dec.isosurface(torch.ones(8, 8, 8).cuda(), 0.0, 1.0)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+    v, f = dec.isosurface(-torch.ones(8, 8, 8).cuda(), 0.0, 1.0)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+    # closed, outward-oriented surface of a sphere: signed volume = +4/3 pi r^3 within the discretisation error
+    n, r = 48, 0.6
+    v, f = dec.isosurface(torch.from_numpy(_sphere(n, r, (0, 0, 0))).cuda(), 0.0, 2.0 / (n - 1), affine_radius=1.0)
+    v, f = v.cpu().numpy().astype(np.float64), f.cpu().numpy()
+    a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    vol = (a * np.cross(b, c)).sum() / 6.0
+    assert abs(vol - 4 / 3 * np.pi * r ** 3) / (4 / 3 * np.pi * r ** 3) < 0.02
+    edges = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    _, counts = np.unique(edges, axis=0, return_counts=True)
+    assert (counts == 2).all(), "the mesh must be watertight (every edge shared by exactly two faces)"
+    assert np.abs(np.linalg.norm(v, axis=1) - r).max() < 2.0 / (n - 1)
+
+
+def test_mesh_extractor_device_path_matches_host_path_on_a_decoder_grid():
+    """MeshExtractor.extract_mesh_from_code (wild_completion/mesher.py:14-24) with the device extractor vs the host
+    extractor on the same decoder SDF grid: same faces, same vertices."""
+    from hortimapping_b200.mesher import MeshExtractor, convert_sdf_voxels_to_mesh
+    from hortimapping_b200 import marching
+    from tests.gpu_helpers import pepper_decoder
+    dec = pepper_decoder()
+    m = load_npz("misc")
+    lat = torch.from_numpy(m["grid_lat"]).cuda()
+    mx = MeshExtractor(dec, code_len=32, voxels_dim=40, cube_radius=0.08, iso="device")
+    mesh = mx.extract_mesh_from_code(lat)
+    sdf = mx.sdf_grid(lat)
+    v_ref, f_ref = marching.marching_tetrahedra(sdf.cpu().numpy(), 0.0, (2.0 / 39,) * 3)
+    v_ref = ((v_ref.astype(np.float64) + -1.0) * 0.08).astype(np.float32)
+    assert mesh.vertices.dtype == np.float32 and mesh.faces.dtype == np.int32
+    np.testing.assert_array_equal(mesh.faces, f_ref)
+    np.testing.assert_allclose(mesh.vertices, v_ref, rtol=0, atol=1e-8)
+    assert mesh.vertices.shape[0] > 1000 and np.abs(mesh.vertices).max() < 0.08
