@@ -10,6 +10,7 @@ from (test_wild_completion.py:15-21, run_shape_completion_challenge.py:14-22):
     wild_completion.optimizer.Optimizer            -> hortimapping_b200.optimizer.Optimizer
     wild_completion.mesher.MeshExtractor           -> hortimapping_b200.mesher.MeshExtractor
     deepsdf.deep_sdf.workspace.{config_decoder,load_latent_vectors} -> hortimapping_b200.decoder
+    metrics_3d.chamfer_distance.ChamferDistance, metrics_3d.precision_recall.PrecisionRecall -> hortimapping_b200.metrics
 """
 from __future__ import annotations
 
@@ -51,6 +52,15 @@ def install(reference_root: str | None = None) -> None:
     mesh_mod = module("wild_completion.mesher", MeshExtractor=_mesher.MeshExtractor)
     loss_mod = module("wild_completion.loss", compute_sdf_loss=_optimizer.compute_sdf_loss, compute_render_loss=_optimizer.compute_render_loss)
     wc.optimizer, wc.mesher, wc.loss = opt_mod, mesh_mod, loss_mod
+    # evaluation metrics (metrics_3d/chamfer_distance.py, precision_recall.py): same classes, GPU nearest neighbours
+    from . import metrics as _metrics
+    try:
+        m3 = importlib.import_module("metrics_3d")
+    except Exception:
+        m3 = module("metrics_3d", MESHTYPE=6, TETRATYPE=10, PCDTYPE=1)
+        m3.__path__ = [os.path.join(reference_root, "metrics_3d")] if reference_root else []
+    m3.chamfer_distance = module("metrics_3d.chamfer_distance", ChamferDistance=_metrics.ChamferDistance)
+    m3.precision_recall = module("metrics_3d.precision_recall", PrecisionRecall=_metrics.PrecisionRecall)
 
 
 def main(argv=None):

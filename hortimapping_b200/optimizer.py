@@ -60,8 +60,9 @@ class PackedBatch:
         self.point_offsets[1:] = np.cumsum([p.shape[0] for p in points])
         self.points = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 3) for p in points], 0))
         self.joint = render_datas is not None
-        self.cube_radius = np.asarray(cube_radius, np.float32).reshape(nf)
-        self.pose_known = np.asarray(pose_known, np.uint8).reshape(nf)
+        # own, contiguous copies: callers may pass scalars broadcast with stride 0, and the C side indexes [fruit]
+        self.cube_radius = np.array(np.broadcast_to(np.asarray(cube_radius, np.float32), (nf,)), np.float32, order="C")
+        self.pose_known = np.array(np.broadcast_to(np.asarray(pose_known, bool), (nf,)), np.uint8, order="C")
         if self.joint:
             T_wc, rays, dobs, n_fg, ray_counts = [], [], [], [], []
             self.frame_offsets = np.zeros(nf + 1, np.int32)

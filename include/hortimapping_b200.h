@@ -159,6 +159,11 @@ int hm_isosurface(hm_context* ctx, const float* d_sdf, int32_t n, double level, 
  * (v - 1) * cube_radius as utils.py:583-585 does. */
 int hm_isosurface_fetch(hm_context* ctx, float* d_verts, int32_t* d_faces, int32_t apply_affine, double cube_radius, void* stream);
 
+/* metrics_3d/chamfer_distance.py:23-24, metrics_3d/precision_recall.py:33-36 (open3d compute_point_cloud_distance):
+ * d_dist[i] = distance from d_query[i] to its nearest neighbour in d_target; fp64, [n][3] row-major, exact. */
+int hm_nn_distance(hm_context* ctx, const double* d_query, int64_t n_query, const double* d_target, int64_t n_target,
+                   double* d_dist, void* stream);
+
 /* wild_completion/loss.py:219-243 compute_sdf_loss: res[n], J_pose[n][pose_dim], J_code[n][32]. */
 int hm_sdf_loss(hm_context* ctx, const float* d_latent, const float* d_pts_obj, int64_t n, int32_t scale_on,
                 float* d_res, float* d_J_pose, float* d_J_code, void* stream);

@@ -8,5 +8,5 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > g
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --iters 40 2>&1 | tail -3 ) > gpurun_out/ncu_launches.log
 ( HM_BENCH_RANDOM_POINTS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_decoder_kernel -s 40 -c 2 \
     -f -o gpurun_out/prof_decoder python bench.py --steps 1 --warmup 1 --iters 30 2>&1 | tail -3 ) > gpurun_out/ncu_full.log
-for s in dbg_wait; do ( timeout 300 python scratch/$s.py 2>&1 | tail -30 ) > gpurun_out/$s.log; done
+( timeout -k 5 600 python scripts/bench_extra.py 2>&1 | grep "^{" ) > gpurun_out/extra.log; cat gpurun_out/extra.log
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.log

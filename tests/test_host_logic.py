@@ -50,6 +50,10 @@ def test_packed_batch_layout():
     np.testing.assert_array_equal(pk.rays[pk.ray_offsets[3]:], pk.rays[:pk.ray_offsets[3]])
     assert pk.pose_known.tolist() == [0, 1] and pk.cube_radius.dtype == np.float32
     # empty render data (no matched frame) is representable: the device loop then reports "submap not valid"
+    # scalars / stride-0 broadcasts must become real per-fruit arrays (the C side indexes them by fruit)
+    pk3 = PackedBatch([c["points_w"]] * 3, [rd] * 3, 3, np.broadcast_to(np.float32(0.08), (3,)), np.broadcast_to(False, (3,)))
+    assert pk3.cube_radius.flags["C_CONTIGUOUS"] and pk3.cube_radius.strides == (4,) and pk3.cube_radius.tolist() == [np.float32(0.08)] * 3
+    assert pk3.pose_known.strides == (1,) and pk3.pose_known.tolist() == [0, 0, 0]
     pk2 = PackedBatch([c["points_w"]], [{k: [] for k in rd}], 10, [0.08], [False])
     assert pk2.frame_offsets.tolist() == [0, 0] and pk2.rays.shape == (0, 3)
 
