@@ -55,7 +55,7 @@ _lib = None
 EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_calibrate",
            "hm_get_counters", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
-           "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance"]
+           "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays"]
 
 
 def lib() -> C.CDLL:
@@ -95,6 +95,11 @@ def lib() -> C.CDLL:
     L.hm_optimize_joint_host.argtypes = [C.c_void_p, C.POINTER(OptParams), C.POINTER(FruitBatch)]
     L.hm_isosurface.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                 C.c_void_p]
+    L.hm_frame_id_bboxes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.hm_crop_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hm_gather_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
     L.hm_nn_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.hm_isosurface_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     _lib = L

@@ -11,6 +11,7 @@ from (test_wild_completion.py:15-21, run_shape_completion_challenge.py:14-22):
     wild_completion.mesher.MeshExtractor           -> hortimapping_b200.mesher.MeshExtractor
     deepsdf.deep_sdf.workspace.{config_decoder,load_latent_vectors} -> hortimapping_b200.decoder
     metrics_3d.chamfer_distance.ChamferDistance, metrics_3d.precision_recall.PrecisionRecall -> hortimapping_b200.metrics
+    wild_completion.utils.get_render_data / get_rays (attributes of the reference's own module) -> hortimapping_b200.render_data
 """
 from __future__ import annotations
 
@@ -61,6 +62,14 @@ def install(reference_root: str | None = None) -> None:
         m3.__path__ = [os.path.join(reference_root, "metrics_3d")] if reference_root else []
     m3.chamfer_distance = module("metrics_3d.chamfer_distance", ChamferDistance=_metrics.ChamferDistance)
     m3.precision_recall = module("metrics_3d.precision_recall", PrecisionRecall=_metrics.PrecisionRecall)
+    # the step before the hot path: wild_completion.utils stays the reference's own module, only get_render_data / get_rays
+    # (utils.py:23-109) are rebound to the device versions (same signature, same dict, same np.random draws)
+    try:
+        from . import render_data as _rd
+        wu = importlib.import_module("wild_completion.utils")
+        wu.get_render_data, wu.get_rays = _rd.get_render_data, _rd.get_rays
+    except Exception:
+        pass      # the reference's utils needs open3d / skimage; without them the host scripts cannot run anyway
 
 
 def main(argv=None):

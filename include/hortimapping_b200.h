@@ -159,6 +159,23 @@ int hm_isosurface(hm_context* ctx, const float* d_sdf, int32_t n, double level, 
  * (v - 1) * cube_radius as utils.py:583-585 does. */
 int hm_isosurface_fetch(hm_context* ctx, float* d_verts, int32_t* d_faces, int32_t apply_affine, double cube_radius, void* stream);
 
+/* wild_completion/utils.py:39-109 get_render_data, device side (ctx may be NULL: current device).
+ * hm_frame_id_bboxes (:48-59): ONE pass over a frame's submap-id image d_id_img [h][w] (int32) and depth image d_depth [h][w]:
+ *   d_table [n_ids][5] = (count, min_v, max_v, min_u, max_u) of the pixels with that id and depth > 0 (count 0: min = INT32_MAX,
+ *   max = -1), for every id < n_ids (<= 1024) at once.
+ * hm_crop_candidates (:66-73, :81-84): the crop grid rows d_hh [crop_h] x columns d_ww [crop_w] in row-major order; background
+ *   candidates (id != submap_id) and foreground candidates (id == submap_id and depth > 0) as [u, v] pixels + depths, in the
+ *   reference's order; d_counts [2] = (n_bg, n_fg).  Output buffers hold crop_h * crop_w entries.
+ * hm_gather_rays (:23-38 get_rays, :74-76, :85-87): for the k selected candidates d_sel (NULL = the first k) the ray directions
+ *   float32(([u, v, 1] * invK).sum(-1)) (fp64 arithmetic, h_invK [9] row-major on the host), depths and pixels. */
+int hm_frame_id_bboxes(hm_context* ctx, const int32_t* d_id_img, const float* d_depth, int32_t h, int32_t w, int32_t n_ids,
+                       int32_t* d_table, void* stream);
+int hm_crop_candidates(hm_context* ctx, const int32_t* d_id_img, const float* d_depth, int32_t h, int32_t w, int32_t submap_id,
+                       const int32_t* d_hh, int32_t crop_h, const int32_t* d_ww, int32_t crop_w, int32_t* d_pix_bg, float* d_depth_bg,
+                       int32_t* d_pix_fg, float* d_depth_fg, int32_t* d_counts, void* stream);
+int hm_gather_rays(hm_context* ctx, const int32_t* d_pix, const float* d_depth, const int64_t* d_sel, int64_t k, const double* h_invK,
+                   float* d_rays, float* d_depth_out, int32_t* d_pix_out, void* stream);
+
 /* metrics_3d/chamfer_distance.py:23-24, metrics_3d/precision_recall.py:33-36 (open3d compute_point_cloud_distance):
  * d_dist[i] = distance from d_query[i] to its nearest neighbour in d_target; fp64, [n][3] row-major, exact. */
 int hm_nn_distance(hm_context* ctx, const double* d_query, int64_t n_query, const double* d_target, int64_t n_target,

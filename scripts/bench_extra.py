@@ -6,6 +6,7 @@ gpurun_out/extra.log -> profiles/.
   grid      hm_sdf_grid 128^3 (BASELINE config 1 grid; fused voxel-grid + decoder forward)      tensor roofline
   iso       hm_isosurface on that grid (device marching tetrahedra) vs the numpy host extractor  HBM-bound integer work
   nn        hm_nn_distance 100k x 100k (Chamfer / precision-recall arithmetic) vs scipy cKDTree
+  render_data  get_render_data for 20 fruits x 10 frames of 720 x 1280 images vs the numpy restatement of the reference
   joint     shape_pose_joint_opt, wild_pepper.yaml sizes (10 frames x 400 rays x 30 samples + 2048 points), 32 fruits
 """
 import copy
@@ -41,7 +42,7 @@ def cuda_ms(fn, reps=5, warm=2):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"grid", "iso", "nn", "joint"}
+    which = set(sys.argv[1:]) or {"grid", "iso", "nn", "joint", "render_data"}
     W, b, codes = B.load_weights()
     dec = Decoder(W, b, device=0)
     g = np.random.default_rng(0)
@@ -77,6 +78,47 @@ def main():
         err = float(np.abs(metrics.nn_distance(da, dc).cpu().numpy() - ref).max())
         print(json.dumps({"what": "hm_nn_distance 100k x 100k (fp64 brute force)", "ms": ms, "pair_evals_per_s": 1e10 / ms * 1e3,
                           "fp64_gflops": 1e10 * 8 / ms / 1e6, "cpu_ckdtree_ms": cpu_ms, "max_abs_diff_vs_ckdtree": err}))
+    if "render_data" in which:
+        from hortimapping_b200 import render_data as RD
+        from oracle import render_data_oracle as RO           # CPU baseline leg only (never on the product path)
+        Hh, Ww, n_fr, n_id = 720, 1280, 10, 20
+        vv, uu = np.mgrid[0:Hh, 0:Ww]
+        id_imgs, depth_imgs, poses = {}, {}, {}
+        for k in range(n_fr):
+            img = np.zeros((Hh, Ww), np.int32)
+            depth = (0.5 + 0.0001 * ((vv * 3 + uu * 5 + k) % 64)).astype(np.float32)
+            for i in range(1, n_id + 1):
+                cv, cu = 90 + 130 * ((i - 1) // 5) + 3 * k, 130 + 250 * ((i - 1) % 5) - 2 * k
+                m = ((vv - cv) / 45.0) ** 2 + ((uu - cu) / 38.0) ** 2 <= 1.0
+                img[m] = i
+                depth[m] = np.float32(0.3 + 0.005 * i)
+            depth[(vv * 7 + uu * 13 + k * 5) % 17 == 0] = 0.0
+            id_imgs[k], depth_imgs[k], poses[k] = img, depth, np.eye(4)
+        invK = np.linalg.inv(np.array([[900.0, 0, 640], [0, 900.0, 360], [0, 0, 1]]))
+        cfg = {"device": "cuda", "opt": {"render": B.WILD_CFG["opt"]["render"]}}
+
+        def run_all(fn):
+            np.random.seed(0)
+            return [fn(i, id_imgs, depth_imgs, poses, (Hh, Ww), invK, cfg) for i in range(1, n_id + 1)]
+        run_all(RD.get_render_data)                             # uploads + per-frame id tables (cached per image object)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev_out = run_all(RD.get_render_data)
+        torch.cuda.synchronize()
+        t_dev = time.perf_counter() - t0
+        RD._frames.clear()
+        t0 = time.perf_counter()
+        dev_cold = run_all(RD.get_render_data)
+        torch.cuda.synchronize()
+        t_cold = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cpu_out = run_all(RO.get_render_data)
+        t_cpu = time.perf_counter() - t0
+        same = all(np.array_equal(a["rays_fg"][j].cpu().numpy(), b2["rays_fg"][j]) and np.array_equal(a["depth_bg"][j].cpu().numpy(), b2["depth_bg"][j])
+                   for a, b2 in zip(dev_out, cpu_out) for j in range(a["count"]))
+        print(json.dumps({"what": f"get_render_data: {n_id} fruits x {n_fr} frames of {Hh}x{Ww} (ids + depth)", "device_s_images_resident": t_dev,
+                          "device_s_including_upload_and_id_tables": t_cold, "cpu_numpy_s": t_cpu, "frames_found": sum(a["count"] for a in dev_out),
+                          "bit_identical_to_cpu": bool(same)}))
     if "joint" in which:
         def sdf_jac(latent, pts):
             y, gr = dec.sdf_jacobian(torch.from_numpy(np.asarray(latent, np.float32)), torch.from_numpy(np.asarray(pts, np.float32)))

@@ -69,7 +69,7 @@ if os.path.exists(rep):
     open(p("ncu_decoder_source_summary.txt"), "w").write(s)
 
 # 4. small logs kept verbatim
-for name in ("pytest_gpu.log", "dbg_rate.log", "dbg_wait.log", "gpu.txt", "scale.log"):
+for name in ("pytest_gpu.log", "dbg_rate.log", "dbg_wait.log", "gpu.txt", "scale.log", "extra.log", "scale_n2.log"):
     f = os.path.join(OUT, name)
     if os.path.exists(f):
         open(p(name.replace(".log", ".txt")), "w").write(open(f).read())
