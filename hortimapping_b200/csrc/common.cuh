@@ -34,19 +34,19 @@ void hm_set_error(const char* fmt, ...);
 
 // ---------------------------------------------------------------------------------------------
 // tensor-core engine: operator list of one tile pass.  An "op" is one fused layer GEMM
-//   D[64 x N] = A[64 x K] * W_op^T  (fp16 hi/lo split operands, fp32 accumulate in TMEM).
+//   D[64 x N] = A[64 x K] * W_op^T  (fp16 hi/lo split operands stacked as 128 MMA rows, fp32 accumulate in TMEM).
 // Forward ops F0..F7 are lin0..lin7; backward ops B7..B0 multiply by the transposed weights.
 // ---------------------------------------------------------------------------------------------
 #define HM_TC_NOPS_FWD 8
 #define HM_TC_NOPS_ALL 16
 #define HM_TC_TILE_M 64          // rows (points) per tile
-#define HM_TC_STAGE_N 128        // weight rows (output features) per pipeline stage
+#define HM_TC_STAGE_N 256        // weight rows (output features) per pipeline stage (64 for B0); a CTA pair splits them
 #define HM_TC_CHUNK_K 64         // K extent of one 128-byte swizzle atom row (fp16)
 
 struct hm_tc_op {
   int32_t n_kchunks;             // K / 64 of the A operand (1 for F0, 8 otherwise)
-  int32_t n_nblocks;             // N / 128 (4; 1 for B0 whose stage holds 64 rows)
-  int32_t stage_rows;            // weight rows per stage (128; 64 for B0)
+  int32_t n_nblocks;             // output halves of stage_rows columns (2; 1 for B0)
+  int32_t stage_rows;            // weight rows per stage = MMA N (256; 64 for B0)
   int32_t pad_;
   float in_scale;                // power of two applied to the A operand before the fp16 split
   float out_unscale;             // 1 / (in_scale * w_scale): turns the accumulator back into fp32 units

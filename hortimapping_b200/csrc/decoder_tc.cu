@@ -1,27 +1,26 @@
-// Tensor-core decoder engine (HM_ENGINE_TC): the whole DeepSDF MLP -- forward and, optionally, the
-// input gradient -- for a tile of 64 query rows in ONE persistent, warp-specialised sm_100a kernel.
+// Tensor-core decoder engine (HM_ENGINE_TC): the whole DeepSDF MLP -- forward and, optionally, the input gradient -- for
+// tiles of 64 query rows per CTA in ONE persistent, warp-specialised sm_100a kernel launched as clusters of two CTAs.
 //
 // Restates deepsdf/networks/deep_sdf_decoder.py:75-110 (forward) and the autograd input gradient of
-// wild_completion/utils.py:112-122,175-193.
+// wild_completion/utils.py:112-122,175-193.  DESIGN.md section 4.1 has the full description and the measurements; in short:
 //
-//   * every layer is a tcgen05.mma GEMM  D[64 x 512] (+)= A[64 x K] * W^T  with fp32 accumulators in
-//     TMEM.  fp32 parity needs more than one fp16/bf16 MMA: operands are split
-//     x*s = hi + lo (fp16 each, s a calibrated power of two) and three MMAs hi*hi + lo*hi + hi*lo are
-//     accumulated -- measured 3e-8 abs SDF error on the shipped decoder, i.e. fp32 grade.
-//   * activations never leave the SM: the epilogue warps read the accumulator from TMEM, apply
-//     bias/ReLU (or the ReLU mask in the backward pass), re-split to fp16 hi/lo and write the next
-//     layer's A operand straight into shared memory in the 128-byte-swizzled K-major UMMA layout.
-//     The next layer's MMAs start per 128-column slice as soon as that slice of A is written.
-//   * the tensor core accumulates fp32 with round-toward-zero (measured: -9e-6 relative after the 96
-//     chained MMAs of one layer), so each 64-wide k-chunk is accumulated into a fresh TMEM buffer
-//     (two 256-column buffers ping-pong; the 64x512 tile is folded onto the 128 TMEM lanes as
-//     2 x (64 rows x 256 columns)) and the chunk partials are summed in registers in fp32 RN.
-//   * weights (pre-split, pre-scaled, pre-swizzled on the host into 32 KB stage blobs in the exact
-//     order the MMA warp consumes them) stream L2 -> shared memory with cp.async.bulk + mbarrier
-//     complete_tx through a 3-stage ring.
+//   * every layer is a tcgen05.mma GEMM with fp32 accumulators in TMEM.  fp32 parity needs more than one fp16/bf16 MMA
+//     (SURVEY.md 7.3): operands are split x*s = hi + lo (fp16 each, s a calibrated power of two); the A tile stacks the hi
+//     and lo rows of the same 64 points as 128 MMA rows and every weight tile exists as a lo and a hi copy, so that
+//     (hi + lo) x (hi + lo) runs at the full-rate shape M = 128 per CTA x N = 256 -- measured 3e-8 abs SDF error, fp32 grade.
+//   * the pair issues cta_group::2 MMAs (M = 256): the B operand is split between the two CTAs' shared memories, each CTA
+//     streams half of every weight tile (cp.async.bulk + mbarrier complete_tx, 6 x 16 KB ring; stages are stored in the blob
+//     pre-swizzled and in consumption order).
+//   * activations never leave the SM: the epilogue warps read partial accumulators from TMEM, apply bias/ReLU (or the ReLU
+//     mask in the backward pass), re-split to fp16 hi/lo and write the next layer's A operand straight into shared memory
+//     in the 128-byte-swizzled K-major UMMA layout, in place.
+//   * the tensor core accumulates fp32 with round-toward-zero (measured: -9e-6 relative after the 96 chained MMAs of one
+//     layer), so MMAs are chained only inside an accumulation group (2 k-chunks x one 256-column output half, 16 MMAs) into
+//     one of two TMEM buffers, and the group partials are summed in registers in fp32 round-to-nearest.
 //
-// Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (+ TMEM alloc),
-// warps 2..9 = epilogue (two per TMEM sub-partition, 128 output columns per thread).
+// Warp roles (640 threads): warpgroup 0 = control (warp 0 bulk-copy producer, warp 1 MMA issuer in the leader CTA / weight
+// arrival forwarder in the peer CTA + TMEM alloc, warps 2-3 idle), warpgroups 1-4 = 16 epilogue warps (4 per TMEM
+// sub-partition, 64 output columns of each half per warp); setmaxnreg moves registers from the control warpgroup to them.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
