@@ -285,11 +285,15 @@ def main():
     rows_per_launch = N_FRUITS * N_PTS
     flop_per_launch = rows_per_launch * FLOP_PER_JAC_ROW
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_file):
+    peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    try:
         pk_json = json.load(open(peaks_file))
-        peak, peak_src = float(pk_json["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-    else:
-        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        for key in ("bf16_tflops_sustained", "bf16_tflops"):       # the kernel is timed inside a long, power-capped step
+            if key in pk_json and float(pk_json[key]) > 0:
+                peak, peak_src = float(pk_json[key]), f"MEASURED_PEAKS.json {key} (of measured)"
+                break
+    except Exception:
+        pass
     achieved = flop_per_launch / (dec_ms / max(n_launch, 1) * 1e-3) / 1e12 if n_launch else None
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")

@@ -102,6 +102,7 @@ def test_fused_grid_equals_explicit_points_and_full_size_grid():
     v, f = dec.isosurface(sdf, 0.0, 2.0 / (n - 1), affine_radius=0.08)
     assert v.shape[0] > 10000 and f.shape[0] > 20000
     assert float(v.abs().max()) <= 0.08 and int(f.min()) == 0 and int(f.max()) == v.shape[0] - 1
-    # every vertex lies on the level set of the trilinear-ish field: its decoded SDF is within one cell of zero
+    # the vertices sit on the level set up to the reference's grid shear (create_voxel_grid quirk, SURVEY.md 7.5: the samples
+    # are taken at sheared positions but meshed as a regular grid -- a few millimetres at this resolution)
     s = dec.sdf(lat, v).abs().max()
-    assert float(s) < 2 * 0.16 / (n - 1)
+    assert float(s) < 0.005
