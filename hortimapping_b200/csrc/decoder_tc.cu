@@ -950,6 +950,64 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int r
   if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tb, 512); }
 }
 
+// CTA-pair probe (cta_group::2): each CTA fills `m_rows` rows of A (64-wide K, SW128) and N/2 rows of B from global memory,
+// the leader issues `reps` x 4 chained MMAs of shape M x N x 16 (M = 2 * m_rows) and both CTAs dump their 128 lanes x 256
+// TMEM columns.  Answers: where does the accumulator of an M = 128 pair MMA (64 rows per CTA) live, and how long does it take?
+__global__ void __launch_bounds__(128, 1) tc_pair_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ out,
+                                                               long long* __restrict__ cycles, int m_rows, int N, int reps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t done_bar;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+  const int nb = N / 2;
+  for (int i = threadIdx.x; i < m_rows * 64; i += 128) *reinterpret_cast<__half*>(smem + sw128_offset(i / 64, i % 64)) = A[(size_t)rank * m_rows * 64 + i];
+  for (int i = threadIdx.x; i < nb * 64; i += 128) *reinterpret_cast<__half*>(smem + 16384 + sw128_offset(i / 64, i % 64)) = B[(size_t)rank * nb * 64 + i];
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<2>(smem_u32(&tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  {
+    uint32_t z = 0x7fc00000u;          // NaN marker: untouched cells stay recognisable
+    for (int c = 0; c < 256; ++c)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tb + ((uint32_t)(32 * warp) << 16) + c), "r"(z) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(2 * m_rows, N);
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
+      for (int ks = 0; ks < 4; ++ks) umma_f16<2>(tb, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (rep | ks) ? 1u : 0u);
+    const long long t1 = clock64();
+    umma_commit<2>(smem_u32(&done_bar));
+    mbar_wait(smem_u32(&done_bar), 0);
+    cycles[0] = t1 - t0;
+    cycles[1] = clock64() - t0;
+  } else {
+    mbar_wait(smem_u32(&done_bar), 0);
+  }
+  __syncthreads();
+  tc_fence_after();
+  for (int q = 0; q < 8; ++q) {
+    float v[32];
+    tmem_ld32(tb + ((uint32_t)(32 * warp) << 16) + q * 32, v);
+    for (int i = 0; i < 32; ++i) out[((size_t)rank * 128 + threadIdx.x) * 256 + q * 32 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<2>(tb, 512); }
+}
+
 // L2 -> shared-memory ingest microbenchmark: every CTA streams `n_stages` stages of `bytes` through a 3-slot ring
 // (no MMAs; the consumer frees a slot as soon as it is full), unicast or multicast over the cluster.
 __global__ void __launch_bounds__(64, 1) tc_ingest_kernel(const uint8_t* blob, int64_t blob_bytes, int n_stages, uint32_t bytes, long long* out) {
@@ -1235,6 +1293,37 @@ extern "C" int hm_debug_tc_mma_rate(hm_context* ctx, int M, int N, int reps, int
   HM_CUDA(cudaDeviceSynchronize());
   HM_CUDA(cudaMemcpy(h_out, d, 16, cudaMemcpyDeviceToHost));
   cudaFree(d);
+  return HM_OK;
+}
+
+// Debug export: h_A [2][m_rows][64], h_B [N][64] fp16 bit patterns, h_out [2][128][256] fp32 TMEM dumps of the two CTAs,
+// h_cycles [2] = (issue, issue + completion) cycles of reps x 4 MMAs.
+extern "C" int hm_debug_tc_pair_probe(hm_context* ctx, const uint16_t* h_A, const uint16_t* h_B, float* h_out, long long* h_cycles, int m_rows,
+                                      int N, int reps) {
+  HM_CHECK(ctx && h_A && h_B && h_out && h_cycles && (m_rows == 64 || m_rows == 128) && N >= 32 && N <= 256 && N % 32 == 0, "hm_debug_tc_pair_probe: bad argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  __half *dA = nullptr, *dB = nullptr;
+  float* dO = nullptr;
+  long long* dC = nullptr;
+  HM_CUDA(cudaMalloc(&dA, 2 * m_rows * 64 * 2));
+  HM_CUDA(cudaMalloc(&dB, N * 64 * 2));
+  HM_CUDA(cudaMalloc(&dO, 2 * 128 * 256 * 4));
+  HM_CUDA(cudaMalloc(&dC, 16));
+  HM_CUDA(cudaMemcpy(dA, h_A, 2 * m_rows * 64 * 2, cudaMemcpyHostToDevice));
+  HM_CUDA(cudaMemcpy(dB, h_B, N * 64 * 2, cudaMemcpyHostToDevice));
+  HM_CUDA(cudaFuncSetAttribute(tc_pair_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 49152; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HM_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_probe_kernel, (const __half*)dA, (const __half*)dB, dO, dC, m_rows, N, reps < 1 ? 1 : reps));
+  HM_CUDA(cudaGetLastError());
+  HM_CUDA(cudaDeviceSynchronize());
+  HM_CUDA(cudaMemcpy(h_out, dO, 2 * 128 * 256 * 4, cudaMemcpyDeviceToHost));
+  HM_CUDA(cudaMemcpy(h_cycles, dC, 16, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
   return HM_OK;
 }
 
