@@ -36,7 +36,8 @@ constexpr int kAChunkBytes = 16384;                // 128 stacked rows (64 point
 constexpr int kSmemA = 0;
 constexpr int kSmemStages = 131072;
 constexpr int kSmemBars = kSmemStages + kWeightRing;             // 229376
-constexpr int kSmemTotal = kSmemBars + 256 + 1024;
+constexpr int kSmemTotal = kSmemBars + 256 + 2048;
+constexpr int kBufs = 4;                           // TMEM accumulator buffers of 128 columns
 constexpr int kEpiWarps = 16;
 constexpr int kCtrlWarps = 4;                      // one full warpgroup: producer, MMA issuer, two idle warps (setmaxnreg is per warpgroup)
 constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
@@ -48,7 +49,7 @@ constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per f
 
 // barrier slots (8 bytes each) inside the barrier block
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = kMaxStages, BAR_A_READY = 2 * kMaxStages, BAR_PART_FULL = BAR_A_READY + 4,
-       BAR_PART_EMPTY = BAR_PART_FULL + 2, BAR_COUNT = BAR_PART_EMPTY + 2 };
+       BAR_PART_EMPTY = BAR_PART_FULL + 4, BAR_COUNT = BAR_PART_EMPTY + 4 };
 static_assert(8 * BAR_COUNT + 4 <= 256, "barrier block overflows into the dot-product scratch");
 
 struct TcParams {
@@ -315,13 +316,13 @@ __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo, uin
   lo = pack_h2_sat(r.x, r.y);
 }
 
-// A-operand row of point p: the tile stacks the fp16 hi parts and the lo parts of the SAME 64 points as 128 MMA
-// rows, so that one full-rate M = 128 MMA multiplies both by a weight tile.  hi of point p sits on row
-// 32*(p/16) + p%16 and its lo on the row 16 below, i.e. both land in the same TMEM sub-partition.
-__host__ __device__ __forceinline__ int a_row(int p, int part) { return 32 * (p >> 4) + 16 * part + (p & 15); }
+// A operand of one k-chunk (16 KB): the fp16 hi parts of the tile's 64 points as one K-major SW128 tile of 64 rows x 64 k
+// (8 KB), followed by the lo parts as a second tile.  A pair MMA of M = 128 takes 64 rows from each CTA, so the hi tile
+// and the lo tile are separate M operands; their products accumulate into the SAME TMEM rows.
+constexpr int kALoOffset = 8192;
 
 // split two scaled fp32 values into packed fp16 hi and lo words (hi = rn(x) saturated to the finite fp16 range,
-// lo = rn(x - hi)) and store them at columns (k, k+1) of point p in chunk `chunk` of the stacked A operand
+// lo = rn(x - hi)) and store them at columns (k, k+1) of point p in chunk `chunk` of the A operand
 __device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int k, float a, float b, int& sat) {
   const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
   sat |= (ac != a) | (bc != b);
@@ -329,8 +330,38 @@ __device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int 
   const float2 hf = __half22float2(hh);
   const __half2 ll = __floats2half2_rn(ac - hf.x, bc - hf.y);
   uint8_t* base = smem + (uint32_t)chunk * kAChunkBytes;
-  *reinterpret_cast<__half2*>(base + sw128_offset(a_row(p, 0), k)) = hh;
-  *reinterpret_cast<__half2*>(base + sw128_offset(a_row(p, 1), k)) = ll;
+  *reinterpret_cast<__half2*>(base + sw128_offset(p, k)) = hh;
+  *reinterpret_cast<__half2*>(base + kALoOffset + sw128_offset(p, k)) = ll;
+}
+
+// wait for all outstanding TMEM loads; the 32 loaded registers pass through the statement so that no consumer can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep32(float (&a)[32]) {
+  uint32_t* x = reinterpret_cast<uint32_t*>(a);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(x[8]), "+r"(x[9]),
+                 "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(x[16]), "+r"(x[17]), "+r"(x[18]), "+r"(x[19]), "+r"(x[20]), "+r"(x[21]), "+r"(x[22]), "+r"(x[23]), "+r"(x[24]),
+                 "+r"(x[25]), "+r"(x[26]), "+r"(x[27]), "+r"(x[28]), "+r"(x[29]), "+r"(x[30]), "+r"(x[31])
+               :
+               : "memory");
+}
+// TMEM -> registers, 32 lanes x 32 consecutive columns (thread = lane = accumulator row), without the wait
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
 // k-chunk order of an 8-chunk op: k-step s multiplies chunks {0,2}, {1,3}, {4,6}, {5,7}.  Steps 0,1 read the chunks that the
@@ -348,31 +379,34 @@ __host__ __device__ __forceinline__ void group_of(int n_kchunks, int n_nblocks, 
   else { step = (0x32321100u >> (4 * g)) & 0xF; nh = (0xCAu >> g) & 1; }
 }
 
-// kPair: the kernel runs as clusters of two CTAs (one TPC).  Each CTA owns a tile of 64 points; the pair issues
-// cta_group::2 MMAs of M = 256 (128 stacked rows per CTA) x N = 256 whose B operand is split between the two CTAs'
-// shared memories, so each CTA streams only HALF of every weight tile from L2 (the single-CTA kernel is bound by the
-// L2 -> shared-memory weight stream: 14.9 MB per 64 points).  CTA rank 0 (the leader) issues all MMAs.
-template <bool kJac, bool kPair>
+// The kernel runs as clusters of two CTAs (one TPC).  Each CTA owns a tile of 64 points; the pair issues cta_group::2 MMAs
+// of M = 128 (64 rows per CTA -- measured: full rate, 64 cycles for N = 256, scratch/dbg_pair_probe.py) whose B operand is
+// split between the two CTAs' shared memories, so each CTA streams only HALF of every weight tile from L2.  Per weight
+// tile pair the THREE needed products are issued -- A_hi x W_lo, A_lo x W_hi, A_hi x W_hi -- into the same accumulator
+// rows (the 64 x N accumulator of each CTA is folded onto 128 lanes x N/2 columns: lanes 0..63 hold output columns
+// [0, N/2), lanes 64..127 columns [N/2, N)).  CTA rank 0 (the leader) issues all MMAs.
+template <bool kJac>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int CG = kPair ? 2 : 1;
-  constexpr int kStages = kPair ? 6 : 3;
-  constexpr int kStageBytes = kWeightRing / kStages;      // 256 / CG output features x 64 k x 2 B (hi OR lo)
+  constexpr int CG = 2;
+  constexpr int kStages = kMaxStages;
+  constexpr int kStageBytes = kWeightRing / kStages;      // 128 output features x 64 k x 2 B (hi OR lo) = this CTA's half of a tile
+  constexpr bool kPair = true;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp index as a uniform value
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
-  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][4 column groups]
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups]
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;                       // 0 = leader (MMA issuer) of the pair
-  const uint32_t lead_bars = kPair ? mapa_rank(bars, 0) : bars;               // the leader's barrier block (cluster address)
+  const uint32_t rank = cluster_ctarank();                                    // 0 = leader (MMA issuer) of the pair
+  const uint32_t lead_bars = mapa_rank(bars, 0);                              // the leader's barrier block (cluster address)
   auto lead_bar = [&](int i) { return lead_bars + 8u * i; };
-  const int64_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_stride = kPair ? (gridDim.x >> 1) : gridDim.x;
-  // debug timeline: (code << 24 | op << 16 | index, clock) pairs of the first CTA (pair); region 0 = MMA issuer,
+  const int64_t unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
+  // debug timeline: (code << 24 | op << 16 | index, clock) pairs of the first CTA pair; region 0 = MMA issuer,
   // 1 / 2 = first epilogue warp of the leader / peer CTA
   constexpr uint32_t kTraceCap = 8192;
-  const bool tracing = P.trace != nullptr && blockIdx.x < (kPair ? 2 : 1);
+  const bool tracing = P.trace != nullptr && blockIdx.x < 2;
   uint32_t trace_n = 0;
   auto trace = [&](int region, uint32_t code, uint32_t op, uint32_t idx) {
     if (tracing && trace_n < kTraceCap) {
@@ -385,63 +419,64 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     // W_FULL of the leader also collects the peer's "my half has landed" arrive
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), (kPair && rank == 0) ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), rank == 0 ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
     for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
+    for (int b = 0; b < kBufs; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(smem_u32((const void*)tmem_ptr_smem), 512);
   tc_fence_before();
   __syncthreads();
-  if constexpr (kPair) cluster_sync_all();        // both CTAs' barriers and TMEM exist before anything crosses the pair
+  cluster_sync_all();        // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (lane == 0 && (warp == 1 || warp == kCtrlWarps)) trace(warp == 1 ? 0 : 1 + rank, 0, 0, 0);     // common time origin
 
   const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
   const int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
-  const int64_t n_units = kPair ? (n_tiles + 1) / 2 : n_tiles;               // a unit = one tile per CTA of the pair
+  const int64_t n_units = (n_tiles + 1) / 2;               // a unit = one tile per CTA of the pair
 
   if (warp < kCtrlWarps) {
-  // the control warpgroup hands most of its registers to the two epilogue warpgroups (128 accumulators per thread)
+  // the control warpgroup hands most of its registers to the four epilogue warpgroups (64 accumulators per thread)
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
-    // ===================== weight producer (every CTA; a pair member fetches its half of each stage) =====================
-    {
-      uint32_t slot = 0, phase = 0;
-      long long t_empty = 0;
-      for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-        for (int op = 0; op < kOps; ++op) {
-          const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t bytes = (uint32_t)o.stage_rows * 128u / CG;     // this CTA's rows of one 64-k fp16 tile
-          const int nst = o.n_kchunks * o.n_nblocks * 2;                 // (chunk, n-half) x {lo, hi}
-          const uint8_t* src = P.blob + o.blob_offset + (size_t)rank * bytes;
-          for (int s = 0; s < nst; ++s) {
-            mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
-            if (elect_one()) {
-              mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
-              bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes * CG, bytes, bar(BAR_W_FULL + slot));
-            }
-            __syncwarp();
-            if (++slot == kStages) { slot = 0; phase ^= 1; }
+    // ===================== weight producer (every CTA fetches its half of each stage) =====================
+    uint32_t slot = 0, phase = 0;
+    long long t_empty = 0;
+    for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
+      for (int op = 0; op < kOps; ++op) {
+        const hm_tc_op& o = P.plan.ops[op];
+        const uint32_t bytes = (uint32_t)o.stage_rows * 128u / CG;     // this CTA's rows of one 64-k fp16 tile
+        const int nst = o.n_kchunks * o.n_nblocks * 2;                 // (chunk, n-half) x {lo, hi}
+        const uint8_t* src = P.blob + o.blob_offset + (size_t)rank * bytes;
+        for (int s = 0; s < nst; ++s) {
+          mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
+          if (elect_one()) {
+            mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+            bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes * CG, bytes, bar(BAR_W_FULL + slot));
           }
+          __syncwarp();
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
         }
       }
-      if (P.flags && rank == 0 && lane == 0) atomicAdd((unsigned long long*)(P.flags + 8), (unsigned long long)t_empty);
     }
+    if (P.flags && rank == 0 && lane == 0) atomicAdd((unsigned long long*)(P.flags + 8), (unsigned long long)t_empty);
   } else if (warp == 1) {
     if (rank == 0) {
       // ===================== MMA issuer (leader CTA; whole warp walks the loops, one elected lane issues) =====================
-      // One accumulation group = (k-step = 2 k-chunks, 256-column output half): 8 MMAs against the lo weight tiles, then 8
-      // against the hi tiles, each M = 128 per CTA (hi rows and lo rows of 64 points) x N = 256 x K = 16, into a FRESH
-      // 256-column TMEM buffer.  The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per
-      // chained MMA), so chains are kept short and the epilogue warps add the group partials in fp32 round-to-nearest.
+      // One accumulation group = (k-step = 2 k-chunks, 256-column output half): per chunk A_hi x W_lo (4 MMAs), then A_lo x W_hi
+      // and A_hi x W_hi (8 MMAs), each M = 64 per CTA x N = 256 x K = 16, into a FRESH 128-column TMEM buffer (four buffers).
+      // The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA), so chains are
+      // kept to one group and the epilogue warps add the group partials in fp32 round-to-nearest.
       uint32_t slot = 0, phase = 0, op_seq = 0, gseq = 0;
-      long long t_a = 0, t_part = 0, t_w = 0, t_begin = clock64();
+      long long t_a = 0, t_part = 0, t_w = 0;
+#ifdef HM_TC_COUNTERS
+      const long long t_begin = clock64();
+#endif
       for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
         for (int op = 0; op < kOps; ++op, ++op_seq) {
           const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t idesc = make_idesc(128 * CG, o.stage_rows);
+          const uint32_t idesc = make_idesc(64 * CG, o.stage_rows);
           const int ng = groups_of(o.n_kchunks, o.n_nblocks);
           const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
           int steps_ready = 0;
@@ -456,25 +491,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               for (; steps_ready <= step; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), op_seq & 1, t_a);
               tc_fence_after();
             }
-            const uint32_t buf = gseq & 1;
+            const uint32_t buf = gseq & (kBufs - 1);
             if (lane == 0) trace(0, 1, op, g);
-            mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq >> 1) & 1) ^ 1, t_part);
+            mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq / kBufs) & 1) ^ 1, t_part);
             tc_fence_after();
             if (lane == 0) trace(0, 2, op, g);
-            const uint32_t d = tmem_base + buf * 256;
+            const uint32_t d = tmem_base + buf * 128;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
               for (int which = 0; which < nwhich; ++which) {
                 const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
-                const uint64_t a_desc = make_desc(smem_base + kSmemA + chunk * kAChunkBytes);
+                const uint64_t a_hi = make_desc(smem_base + kSmemA + chunk * kAChunkBytes);
+                const uint64_t a_lo = a_hi + (kALoOffset >> 4);
                 const uint64_t w_desc = make_desc(smem_base + kSmemStages + slot * kStageBytes);
                 mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
                 tc_fence_after();
                 if (elect_one()) {
+                  if (part == 0) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)                     // +32 B per 16-wide k step = +2 in the descriptor's address field
-                    umma_f16<CG>(d, a_desc + 2 * ks, w_desc + 2 * ks, idesc, (part | which | ks) ? 1u : 0u);
-                  umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of a pair
+                    for (int ks = 0; ks < 4; ++ks)                   // +32 B per 16-wide k step = +2 in the descriptor's address field
+                      umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, (which | ks) ? 1u : 0u);
+                  } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_lo + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+                  }
+                  umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of the pair
                   if (part == 1 && which == nwhich - 1) umma_commit<CG>(bar(BAR_PART_FULL + buf));
                 }
                 __syncwarp();
@@ -485,13 +528,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           }
         }
       }
+#ifdef HM_TC_COUNTERS
       if (P.flags && lane == 0) {
         atomicAdd((unsigned long long*)(P.flags + 10), (unsigned long long)t_a);
         atomicAdd((unsigned long long*)(P.flags + 12), (unsigned long long)t_part);
         atomicAdd((unsigned long long*)(P.flags + 14), (unsigned long long)t_w);
         atomicAdd((unsigned long long*)(P.flags + 16), (unsigned long long)(clock64() - t_begin));
       }
-    } else if (kPair) {
+#endif
+    } else {
       // ===================== peer CTA: tell the leader that this CTA's half of a weight stage has landed =====================
       uint32_t slot = 0, phase = 0;
       for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
@@ -511,18 +556,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     // ===================== epilogue warps (16) =====================
-    // Warp (sp, h4): TMEM sub-partition sp = warp % 4 holds the hi rows (lanes 0..15) and lo rows (lanes 16..31) of
-    // points 16*sp .. 16*sp+15; column group h4 owns columns [64*h4, +64) of each 256-column output half, i.e. exactly
-    // k-chunk 4*nh + h4 of the next op's A operand.  With the 16x256b load shape thread t holds points pA = 16*sp + t/4
-    // and pB = pA + 8, columns 8e + 2(t%4) + {0,1}: the hi-row and lo-row results of one (point, column) arrive in the
-    // SAME thread and are summed there.  Four warps per scheduler keep the (latency-bound) conversion code busy.
+    // TMEM sub-partition sp = warp % 4 (lanes 32*sp ..): lanes 0..63 hold the tile's 64 points for output columns [0, 128) of
+    // a 256-column half, lanes 64..127 the same points for columns [128, 256).  So a thread is ONE point (p = 32*(sp & 1) +
+    // lane), hq = sp / 2 selects the 128-column quarter and the four warps of a sub-partition split its 128 TMEM columns
+    // (cq = 0..3, 32 columns each): a thread owns 32 CONSECUTIVE output columns of each half = half a k-chunk row of the next
+    // op's A operand, which it writes with four 16-byte stores for the hi and four for the lo part.
     const int e_w = warp - kCtrlWarps;
     const int sp = warp & 3;
-    const int h4 = e_w >> 2;
-    const int tq = lane & 3;                 // column pair inside an 8-column block
-    const int pA = 16 * sp + (lane >> 2), pB = pA + 8;
-    const uint32_t t_hi = tmem_base + ((uint32_t)(32 * sp) << 16) + 64 * h4;
-    const uint32_t t_lo = t_hi + (16u << 16);
+    const int hq = sp >> 1;
+    const int cq = e_w >> 2;
+    const int g8 = 4 * hq + cq;              // this thread's column group among the 8 of a half
+    const int p = 32 * (sp & 1) + lane;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(32 * sp) << 16) + 32 * cq;
     uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 2;   // [op][thread][2 words]
     constexpr size_t kMaskStride = (size_t)kEpiWarps * 32 * 2;
     uint32_t op_seq = 0, gseq = 0;
@@ -534,62 +579,57 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     auto publish = [&](int j) {              // this warp's part of k-step j of the next A operand is written
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_A_READY + j)); else mbar_arrive(bar(BAR_A_READY + j)); }
+      if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_A_READY + j));
     };
-    // Column (within the 512-wide layer) of accumulator pair i = 8*nh + 4*cb + e: 256*nh + 64*h4 + 32*cb + 8*e + 2*tq.
-    // Its A-operand address: chunk 4*nh + h4, 16-byte unit 4*cb + e (XOR row & 7), byte 4*tq.
-    auto col_of = [&](int nh, int cb, int e) { return 256 * nh + 64 * h4 + 32 * cb + 8 * e + 2 * tq; };
-    const uint32_t r7 = (uint32_t)(lane >> 2) & 7u;
-    uint8_t* const st_base = smem + kSmemA + (uint32_t)h4 * kAChunkBytes + 4 * tq +
-                             (uint32_t)(a_row(pA, 0) >> 3) * 1024 + (a_row(pA, 0) & 7) * 128;      // hi row of point A
+    // First of this thread's 32 consecutive columns of output half nh (within the 512-wide layer), and where they go in the
+    // next A operand: chunk 4*nh + 2*hq + cq/2, k = 32*(cq & 1) + j, i.e. 16-byte units 4*(cq & 1) .. +3 of row p.
+    auto col0_of = [&](int nh) { return 256 * nh + 128 * hq + 32 * cq; };
+    uint8_t* const st_row = smem + kSmemA + (uint32_t)(2 * hq + (cq >> 1)) * kAChunkBytes + (uint32_t)(p >> 3) * 1024 + (p & 7) * 128;
+    const uint32_t u_base = 4 * (cq & 1), r7 = (uint32_t)p & 7u;
     uint32_t sat2 = 0;
-    auto store2 = [&](int nh, int cb, int e, float2 va, float2 vb) {
-      const uint32_t off = (uint32_t)(4 * nh) * kAChunkBytes + (((uint32_t)(4 * cb + e) ^ r7) << 4);
-      uint32_t ha, la, hb, lb;
-      split2(va, ha, la, sat2);
-      split2(vb, hb, lb, sat2);
-      *reinterpret_cast<uint32_t*>(st_base + off) = ha;                 // rows: A hi, +16 rows A lo, +8 rows B hi, +24 rows B lo
-      *reinterpret_cast<uint32_t*>(st_base + off + 2048) = la;
-      *reinterpret_cast<uint32_t*>(st_base + off + 1024) = hb;
-      *reinterpret_cast<uint32_t*>(st_base + off + 3072) = lb;
+    // split 8 consecutive values (one 16-byte unit u = 0..3 of this thread's 32 columns) and store the hi and lo units
+    auto emit_unit = [&](int nh, int u, const float (&y)[8]) {
+      uint4 hi, lo;
+      split2(make_float2(y[0], y[1]), hi.x, lo.x, sat2);
+      split2(make_float2(y[2], y[3]), hi.y, lo.y, sat2);
+      split2(make_float2(y[4], y[5]), hi.z, lo.z, sat2);
+      split2(make_float2(y[6], y[7]), hi.w, lo.w, sat2);
+      uint8_t* dst = st_row + (uint32_t)(4 * nh) * kAChunkBytes + (((u_base + (uint32_t)u) ^ r7) << 4);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + kALoOffset) = lo;
     };
     for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-      const int64_t tile = kPair ? 2 * unit + rank : unit;       // the odd CTA of the last pair may get an all-padding tile
-      const int64_t growA = tile * HM_TC_TILE_M + pA, growB = tile * HM_TC_TILE_M + pB;
-      const bool okA = growA < n_rows, okB = growB < n_rows;
-      // raw input x0 = [latent(32), xyz(3)] of the two points of this thread (deep_sdf_decoder.py:76-88); the pointers
-      // are rebuilt where they are needed (tile start, the skip-concat columns) instead of living in registers
-      const int64_t lrA = okA ? growA : (n_rows - 1), lrB = okB ? growB : (n_rows - 1);
-      const int32_t liA = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lrA) : 0;      // latent-table row of each point
-      const int32_t liB = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lrB) : 0;
-      auto x0 = [&](int64_t lr, int32_t li, int k) -> float {
+      const int64_t tile = 2 * unit + rank;       // the odd CTA of the last pair may get an all-padding tile
+      const int64_t grow = tile * HM_TC_TILE_M + p;
+      const bool ok = grow < n_rows;
+      // raw input x0 = [latent(32), xyz(3)] of this thread's point (deep_sdf_decoder.py:76-88)
+      const int64_t lr = ok ? grow : (n_rows - 1);
+      const int32_t li = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lr) : 0;      // latent-table row of the point
+      auto x0 = [&](int k) -> float {
         if (k >= HM_IN) return 0.f;
         if (P.rows) return __ldg(P.rows + lr * HM_IN + k);
         if (k < HM_LATENT) return __ldg(P.latents + (size_t)li * HM_LATENT + k);
         if (P.grid_n > 0) return hm_grid_coord(lr, k - HM_LATENT, P.grid_n, P.grid_voxel, P.grid_radius);
         return __ldg(P.xyz + lr * 3 + (k - HM_LATENT));
       };
-      auto x0A = [&](int k) { return x0(lrA, liA, k); };
-      auto x0B = [&](int k) { return x0(lrB, liB, k); };
-      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group h4 writes k in [16*h4, +16)
+      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group g8 writes k in [8*g8, +8)
       {
         const float s0 = P.plan.ops[0].in_scale;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 16 * h4 + 8 * e + 2 * tq;
-          store_pair(smem, 0, pA, k, x0A(k) * s0, x0A(k + 1) * s0, sat);
-          store_pair(smem, 0, pB, k, x0B(k) * s0, x0B(k + 1) * s0, sat);
+        for (int e = 0; e < 4; ++e) {
+          const int k = 8 * g8 + 2 * e;
+          store_pair(smem, 0, p, k, x0(k) * s0, x0(k + 1) * s0, sat);
         }
         for (int j = 0; j < 4; ++j) publish(j);
       }
-      float fA = 0.f, fB = 0.f;
-      // Accumulators of this thread, as column pairs: acc[8*nh + 4*cb + e] = columns col_of(nh, cb, e) + {0, 1}.  They and
-      // the ReLU bits live across op boundaries: output half 1 of an op is finalized only after the first partial of the
-      // NEXT op has been collected (schedule below), so that the tensor core never waits for it.
-      float2 accA[16], accB[16];
-      uint32_t mA = 0u, mB = 0u;             // ReLU bits of the current op: bits 0..15 output half 0, bits 16..31 half 1
-      uint32_t pmA = 0u, pmB = 0u;           // ... of the previous op (for its deferred half 1)
-      float dotA = 0.f, dotB = 0.f;
+      float f_out = 0.f;
+      // Accumulators of this thread: acc[nh][i] = columns col0_of(nh) + 2i + {0, 1}.  They and the ReLU bits live across op
+      // boundaries: output half 1 of an op is finalized only after the first partial of the NEXT op has been collected
+      // (schedule below), so that the tensor core never waits for it.
+      float2 acc[2][16];
+      uint32_t m0 = 0u, m1 = 0u;             // ReLU bits of the current op: output half 0 / half 1, bit j = column col0 + j
+      uint32_t pm1 = 0u;                     // half-1 bits of the previous op (for its deferred half)
+      float dot = 0.f;
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
       const std::integral_constant<int, 2> I2{};
@@ -599,60 +639,48 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const float unscale = o.out_unscale;
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
         const float k_mul = unscale * s_next;
-        const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns, one group per step, column group 0 only
+        const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns (32 TMEM columns), one group per step
         const bool wide = (o.n_kchunks != 1);
         const bool has_pending = (op != 0 && op != 8);   // the previous op left its output half 1 to this one
         const bool defer = (op != 7 && op != 15);        // ... and this op leaves its own to the next
-        pmA = mA; pmB = mB;
-        mA = mB = 0u;
+        pm1 = m1;
+        m0 = m1 = 0u;
         if (kJac && op >= 8 && op < 15) {
           const uint2 mw = *reinterpret_cast<const uint2*>(my_masks + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
-          mA = mw.x; mB = mw.y;
+          m0 = mw.x; m1 = mw.y;
         }
-        // collect the partial accumulator of one (step, n-half) group: hi-row and lo-row results meet in this thread.
-        // FIRST: the group opens the op for this output half (overwrite instead of accumulate).
+        // collect the partial accumulator of one (step, n-half) group.  FIRST: the group opens the op for this output half
+        // (overwrite instead of accumulate).
         auto promote = [&](auto NH, auto FIRST) {
           constexpr int nh = decltype(NH)::value;
           constexpr bool first = decltype(FIRST)::value != 0;
-          const uint32_t buf = gseq & 1;
+          const uint32_t buf = gseq & (kBufs - 1);
 #ifdef HM_TC_COUNTERS
           const long long tp0 = clock64();
 #endif
-          mbar_wait(bar(BAR_PART_FULL + buf), (gseq >> 1) & 1);
+          mbar_wait(bar(BAR_PART_FULL + buf), (gseq / kBufs) & 1);
 #ifdef HM_TC_COUNTERS
           const long long tp1 = clock64();
           t_pfull += tp1 - tp0;
 #endif
           tc_fence_after();
           if (e_w == 0 && lane == 0) trace(1 + rank, 10, op, gseq & 0xffff);
-          // two 32-column pieces of this warp's 64 columns (narrow B0: column group 0 only)
-          const uint32_t t_h = t_hi + buf * 256, t_l = t_lo + buf * 256;
           auto release = [&]() {               // all TMEM reads of this buffer are complete
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if constexpr (kPair) mbar_arrive_cluster(lead_bar(BAR_PART_EMPTY + buf)); else mbar_arrive(bar(BAR_PART_EMPTY + buf)); }
+            if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_PART_EMPTY + buf));
           };
-          if (narrow && h4 != 0) {
+          if (narrow && cq != 0) {             // B0's 64 output columns occupy TMEM columns 0..31 only
             release();
           } else {
+            float v[32];
+            tmem_ld32_nowait(t_addr + buf * 128, v);
+            tmem_ld_wait_dep32(v);
+            release();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float2 vh[8], vl[8];
-              tmem_ld_16x256b_x4(t_h + 32 * c, reinterpret_cast<float*>(vh));
-              tmem_ld_16x256b_x4(t_l + 32 * c, reinterpret_cast<float*>(vl));
-              tmem_ld_wait_dep(vh, vl);
-              if (c == 1) release();
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {        // v[2q] = point A pair, v[2q+1] = point B pair
-                const int i = 8 * nh + 4 * c + q;
-                if constexpr (first) {
-                  accA[i] = add2(vh[2 * q], vl[2 * q]);
-                  accB[i] = add2(vh[2 * q + 1], vl[2 * q + 1]);
-                } else {
-                  accA[i] = add2(accA[i], add2(vh[2 * q], vl[2 * q]));
-                  accB[i] = add2(accB[i], add2(vh[2 * q + 1], vl[2 * q + 1]));
-                }
-              }
+            for (int i = 0; i < 16; ++i) {
+              const float2 w = make_float2(v[2 * i], v[2 * i + 1]);
+              if constexpr (first) acc[nh][i] = w; else acc[nh][i] = add2(acc[nh][i], w);
             }
           }
           ++gseq;
@@ -661,106 +689,92 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #endif
           if (e_w == 0 && lane == 0) trace(1 + rank, 12, op, gseq & 0xffff);
         };
-        // Turn the finished output half nh of op `opx` into the next op's A chunk 4*nh + h4 (k-steps 2*nh, 2*nh+1) or the
+        // Turn the finished output half nh of op `opx` into the next op's A chunks 4*nh .. 4*nh+3 (k-steps 2*nh, 2*nh+1) or the
         // final outputs.  kClass: 0 = any op, 1 = opx is a hidden layer (forward or backward: the deferred half), 2 = lin7.
-        auto finalize = [&](auto NH, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x,
-                            uint32_t& mA_, uint32_t& mB_) {
+        auto finalize = [&](auto NH, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x, uint32_t& m_) {
           constexpr int nh = decltype(NH)::value, kClass = decltype(CLASS)::value;
 #ifdef HM_TC_COUNTERS
           const long long tf0 = clock64();
 #endif
           if (e_w == 0 && lane == 0) trace(1 + rank, 13, opx, nh);
+          const int col0 = col0_of(nh);
           if (kClass != 2 && opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
-            const float* bias = P.bias + opx * HM_HIDDEN;
+            const float* bias = P.bias + opx * HM_HIDDEN + col0;
             const float2 kk = make_float2(k_mul_x, k_mul_x);
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
+            for (int u = 0; u < 4; ++u) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * u)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * u + 4));
+              float2 y0 = fma2(acc[nh][4 * u + 0], kk, make_float2(b0.x, b0.y)), y1 = fma2(acc[nh][4 * u + 1], kk, make_float2(b0.z, b0.w));
+              float2 y2 = fma2(acc[nh][4 * u + 2], kk, make_float2(b1.x, b1.y)), y3 = fma2(acc[nh][4 * u + 3], kk, make_float2(b1.z, b1.w));
+              const float y[8] = {y0.x, y0.y, y1.x, y1.y, y2.x, y2.y, y3.x, y3.y};
+              float r[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
-                const int col = col_of(nh, cb, e);
-                const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
-                float2 ya = fma2(accA[i], kk, bz), yb = fma2(accB[i], kk, bz);
-                mA_ |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
-                mB_ |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
-                ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                store2(nh, cb, e, ya, yb);
+              for (int i = 0; i < 8; ++i) {
+                m_ |= ((y[i] > 0.f) ? 1u : 0u) << (8 * u + i);
+                r[i] = fmaxf(y[i], 0.f);
               }
+              emit_unit(nh, u, r);
             }
-            if (nh == 1 && opx == 3 && h4 == 3) {
+            if (nh == 1 && opx == 3 && hq == 1 && cq >= 2) {
               // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat, deep_sdf_decoder.py:87-88).
-              // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the last
-              // column group rewrites its elements from column 476 on and clears their ReLU bits.
+              // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the threads that
+              // own columns >= 477 rewrite those units and clear their ReLU bits.
 #pragma unroll
-              for (int cb = 0; cb < 2; ++cb) {
+              for (int u = 0; u < 4; ++u) {            // static indices keep the accumulators in registers
+                if (cq == 2 && u < 3) continue;
+                float r[8];
 #pragma unroll
-                for (int e = (cb == 0 ? 3 : 0); e < 4; ++e) {
-                  const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
-                  const int col = col_of(nh, cb, e);
-                  if (col + 1 >= HM_SKIP_COL) {
-                    float2 ya, yb;
-                    if (col >= HM_SKIP_COL) {
-                      ya.x = x0A(col - HM_SKIP_COL) * s_next_x; yb.x = x0B(col - HM_SKIP_COL) * s_next_x;
-                      mA_ &= ~(1u << bit); mB_ &= ~(1u << bit);
-                    } else {                        // column 476: the last real lin3 output
-                      const float bz = __ldg(bias + col);
-                      ya.x = fmaxf(fmaf(accA[i].x, k_mul_x, bz), 0.f); yb.x = fmaxf(fmaf(accB[i].x, k_mul_x, bz), 0.f);
-                    }
-                    ya.y = x0A(col + 1 - HM_SKIP_COL) * s_next_x; yb.y = x0B(col + 1 - HM_SKIP_COL) * s_next_x;
-                    mA_ &= ~(1u << (bit + 1)); mB_ &= ~(1u << (bit + 1));
-                    store2(nh, cb, e, ya, yb);
+                for (int i = 0; i < 8; ++i) {
+                  const int j = 8 * u + i, col = col0 + j;
+                  if (col >= HM_SKIP_COL) {
+                    r[i] = x0(col - HM_SKIP_COL) * s_next_x;
+                    m_ &= ~(1u << j);
+                  } else {
+                    const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
+                    r[i] = fmaxf(fmaf(a, k_mul_x, __ldg(bias + j)), 0.f);
                   }
                 }
+                emit_unit(nh, u, r);
               }
             }
             publish(2 * nh); publish(2 * nh + 1);
           } else if (kClass != 1 && opx == 7) {
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
-            const float* bias = P.bias + 7 * HM_HIDDEN;
+            const float* bias = P.bias + 7 * HM_HIDDEN + col0;
+            const float* w8 = P.w8 + col0;
             const float2 uu = make_float2(unscale_x, unscale_x);
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) {
-              const int i = 8 * nh + ii, bit = 16 * nh + 2 * ii;
-              const int col = col_of(nh, ii >> 2, ii & 3);
-              const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + col));
-              const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col));
-              const float2 ya = fma2(accA[i], uu, bz), yb = fma2(accB[i], uu, bz);
-              mA_ |= ((ya.x > 0.f) ? 1u : 0u) << bit | ((ya.y > 0.f) ? 1u : 0u) << (bit + 1);
-              mB_ |= ((yb.x > 0.f) ? 1u : 0u) << bit | ((yb.y > 0.f) ? 1u : 0u) << (bit + 1);
-              dotA = fmaf(fmaxf(ya.x, 0.f), wz.x, dotA); dotA = fmaf(fmaxf(ya.y, 0.f), wz.y, dotA);
-              dotB = fmaf(fmaxf(yb.x, 0.f), wz.x, dotB); dotB = fmaf(fmaxf(yb.y, 0.f), wz.y, dotB);
+            for (int i = 0; i < 16; ++i) {
+              const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + 2 * i));
+              const float2 wz = __ldg(reinterpret_cast<const float2*>(w8 + 2 * i));
+              const float2 y = fma2(acc[nh][i], uu, bz);
+              m_ |= ((y.x > 0.f) ? 1u : 0u) << (2 * i) | ((y.y > 0.f) ? 1u : 0u) << (2 * i + 1);
+              dot = fmaf(fmaxf(y.x, 0.f), wz.x, dot);
+              dot = fmaf(fmaxf(y.y, 0.f), wz.y, dot);
             }
           } else if (kClass != 2 && opx > 7 && opx < 15) {
             // ---------------- backward through lin_l (l = 15 - opx = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
+            for (int u = 0; u < 4; ++u) {
+              float r[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 8 * nh + 4 * cb + e, bit = 16 * nh + 8 * cb + 2 * e;
-                const float2 sa = make_float2(((mA_ >> bit) & 1u) ? k_mul_x : 0.f, ((mA_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
-                const float2 sb = make_float2(((mB_ >> bit) & 1u) ? k_mul_x : 0.f, ((mB_ >> (bit + 1)) & 1u) ? k_mul_x : 0.f);
-                store2(nh, cb, e, make_float2(accA[i].x * sa.x, accA[i].y * sa.y), make_float2(accB[i].x * sb.x, accB[i].y * sb.y));
+              for (int i = 0; i < 8; ++i) {
+                const int j = 8 * u + i;
+                const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
+                r[i] = a * (((m_ >> j) & 1u) ? k_mul_x : 0.f);
               }
+              emit_unit(nh, u, r);
             }
-            if (nh == 1 && opx == 11 && h4 == 3) {
+            if (nh == 1 && opx == 11 && hq == 1 && cq >= 2) {
               // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0 (deep_sdf_decoder.py:87-88).
               // They are parked in the output Jacobian row; B0 adds the rest.  (Their ReLU bits are clear, so the loop above wrote
               // zeros for them into the next A operand.)
+              if (ok) {
 #pragma unroll
-              for (int cb = 0; cb < 2; ++cb) {
-#pragma unroll
-                for (int e = (cb == 0 ? 3 : 0); e < 4; ++e) {
-                  const int i = 8 * nh + 4 * cb + e;
-                  const int col = col_of(nh, cb, e);
-                  if (col >= HM_SKIP_COL) {
-                    if (okA) __stcg(P.jac + growA * HM_IN + (col - HM_SKIP_COL), accA[i].x * unscale_x);
-                    if (okB) __stcg(P.jac + growB * HM_IN + (col - HM_SKIP_COL), accB[i].x * unscale_x);
-                  }
-                  if (col + 1 >= HM_SKIP_COL) {
-                    if (okA) __stcg(P.jac + growA * HM_IN + (col + 1 - HM_SKIP_COL), accA[i].y * unscale_x);
-                    if (okB) __stcg(P.jac + growB * HM_IN + (col + 1 - HM_SKIP_COL), accB[i].y * unscale_x);
-                  }
+                for (int j = 0; j < 32; ++j) {
+                  const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
+                  if (col0 + j >= HM_SKIP_COL) __stcg(P.jac + grow * HM_IN + (col0 + j - HM_SKIP_COL), a * unscale_x);
                 }
               }
               __threadfence_block();
@@ -780,8 +794,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         promote(I0, I1);
         if (has_pending) {
           const float q_unscale = P.plan.ops[op - 1].out_unscale;
-          finalize(I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pmA, pmB);
-          if (kJac && op - 1 < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)(op - 1) * kMaskStride) = make_uint2(pmA, pmB);
+          finalize(I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pm1);
+          if (kJac && op - 1 < 7) my_masks[(size_t)(op - 1) * kMaskStride + 1] = pm1;
         }
         if (narrow) {
 #pragma unroll 1
@@ -792,56 +806,50 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           } else {
             promote(I1, I1);       // F0: both output halves read A chunk 0 -- collect both before it is overwritten
           }
-          finalize(I0, I0, op, k_mul, unscale, s_next, mA, mB);
+          finalize(I0, I0, op, k_mul, unscale, s_next, m0);
+          if (kJac && op < 7) my_masks[(size_t)op * kMaskStride] = m0;
           if (wide) { promote(I1, I0); promote(I1, I0); }
-          if (!defer) finalize(I1, I2, op, k_mul, unscale, s_next, mA, mB);
+          if (!defer) finalize(I1, I2, op, k_mul, unscale, s_next, m1);
         }
         if (op == 7) {
-          dotA += __shfl_xor_sync(0xffffffffu, dotA, 1); dotA += __shfl_xor_sync(0xffffffffu, dotA, 2);
-          dotB += __shfl_xor_sync(0xffffffffu, dotB, 1); dotB += __shfl_xor_sync(0xffffffffu, dotB, 2);
-          if (tq == 0) { dot_scratch[pA * 4 + h4] = dotA; dot_scratch[pB * 4 + h4] = dotB; }
+          dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           const float b8 = __ldg(P.b8);
-          const float4 dA = *reinterpret_cast<const float4*>(dot_scratch + pA * 4), dB = *reinterpret_cast<const float4*>(dot_scratch + pB * 4);
-          fA = tanhf(((dA.x + dA.y) + (dA.z + dA.w)) + b8);
-          fB = tanhf(((dB.x + dB.y) + (dB.z + dB.w)) + b8);
+          const float4 d0 = *reinterpret_cast<const float4*>(dot_scratch + p * 8), d1 = *reinterpret_cast<const float4*>(dot_scratch + p * 8 + 4);
+          f_out = tanhf((((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w))) + b8);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          dotA = dotB = 0.f;
-          if (h4 == 0 && tq == 0) {
-            if (okA) P.sdf[growA] = fA;
-            if (okB) P.sdf[growB] = fB;
-          }
+          dot = 0.f;
+          if (g8 == 0 && ok) P.sdf[grow] = f_out;
           if (kJac) {
             // d7 = (1 - f^2) * w8 * relu'(h7): A operand of B7
-            const float cA = (1.f - fA * fA) * s_next, cB = (1.f - fB * fB) * s_next;
+            const float c7 = (1.f - f_out * f_out) * s_next;
 #pragma unroll
             for (int nh = 0; nh < 2; ++nh) {
+              const uint32_t m_ = nh ? m1 : m0;
+              const float* w8 = P.w8 + col0_of(nh);
 #pragma unroll
-              for (int cb = 0; cb < 2; ++cb) {
+              for (int u = 0; u < 4; ++u) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w8 + 8 * u)), w1 = __ldg(reinterpret_cast<const float4*>(w8 + 8 * u + 4));
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                float r[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int bit = 16 * nh + 8 * cb + 2 * e;
-                  const float2 wz = __ldg(reinterpret_cast<const float2*>(P.w8 + col_of(nh, cb, e)));
-                  store2(nh, cb, e, make_float2(((mA >> bit) & 1u) ? cA * wz.x : 0.f, ((mA >> (bit + 1)) & 1u) ? cA * wz.y : 0.f),
-                         make_float2(((mB >> bit) & 1u) ? cB * wz.x : 0.f, ((mB >> (bit + 1)) & 1u) ? cB * wz.y : 0.f));
-                }
+                for (int i = 0; i < 8; ++i) r[i] = ((m_ >> (8 * u + i)) & 1u) ? c7 * w[i] : 0.f;
+                emit_unit(nh, u, r);
               }
               publish(2 * nh); publish(2 * nh + 1);
             }
           }
         } else if (op == 15) {
-          // ---------------- B0: g = d0 W0 (35 valid of 64 columns, all owned by column group 0) + the parked skip gradient
-          if (h4 == 0) {
+          // ---------------- B0: g = d0 W0 (35 valid of 64 columns: TMEM columns 0..31 of lanes 0..63 hold columns 0..31, of
+          //                  lanes 64..127 columns 32..63) + the parked skip gradient
+          if (cq == 0 && ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {              // nh = 0, cb = 0,1: columns 32*cb + 8*e + 2*tq + {0,1} < 64
-              const int col = 32 * (i >> 2) + 8 * (i & 3) + 2 * tq;
+            for (int j = 0; j < 32; ++j) {
+              const int col = 32 * hq + j;
               if (col < HM_IN) {
-                if (okA) { float* q = P.jac + growA * HM_IN + col; *q = fmaf(accA[i].x, unscale, __ldcg(q)); }
-                if (okB) { float* q = P.jac + growB * HM_IN + col; *q = fmaf(accB[i].x, unscale, __ldcg(q)); }
-              }
-              if (col + 1 < HM_IN) {
-                if (okA) { float* q = P.jac + growA * HM_IN + col + 1; *q = fmaf(accA[i].y, unscale, __ldcg(q)); }
-                if (okB) { float* q = P.jac + growB * HM_IN + col + 1; *q = fmaf(accB[i].y, unscale, __ldcg(q)); }
+                const float a = (j & 1) ? acc[0][j >> 1].y : acc[0][j >> 1].x;
+                float* q = P.jac + grow * HM_IN + col;
+                *q = fmaf(a, unscale, __ldcg(q));
               }
             }
           }
@@ -860,7 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (kPair) cluster_sync_all();        // the peer's TMEM / shared memory stay valid until both CTAs are done
+  cluster_sync_all();        // the peer's TMEM / shared memory stay valid until both CTAs are done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, 512);
@@ -1076,13 +1084,6 @@ void fill_tile(uint8_t* dst, int rows, float scale, int part, F&& get) {
 
 }  // namespace
 
-// CTA-pair mode (cta_group::2 MMAs, weights split across the pair) is the product path; HM_TC_PAIR=0 selects the
-// single-CTA variant of the same kernel for A/B measurements.
-static bool hm_tc_pair_mode() {
-  const char* e = getenv("HM_TC_PAIR");
-  return !(e && atoi(e) == 0);
-}
-
 static int hm_tc_blob_copies() {
   const char* e = getenv("HM_TC_BLOB_COPIES");
   int c = e ? atoi(e) : 1;
@@ -1147,10 +1148,8 @@ int hm_tc_init(hm_context* ctx) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * 64));
     HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * 64));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   }
   std::vector<float> bias(8 * HM_HIDDEN, 0.f);
   for (int l = 0; l < 8; ++l) {
@@ -1201,8 +1200,7 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.grid_radius = rows.grid_radius;
   P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
-  const bool pair = hm_tc_pair_mode();
-  const int csize = pair ? 2 : 1;
+  const int csize = 2;                                              // the kernel is a CTA-pair kernel
   const int64_t n_units = (n_tiles + csize - 1) / csize;             // a unit = one 64-row tile per CTA of the cluster
   const int grid = (int)std::min<int64_t>(n_units, ctx->sm_count / csize) * csize;
   cudaLaunchConfig_t cfg = {};
@@ -1217,13 +1215,8 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (pair) {
-    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, true>, P));
-    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, true>, P));
-  } else {
-    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, false>, P));
-    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, false>, P));
-  }
+  if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true>, P));
+  else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false>, P));
   ctx->counters.kernel_launches += 1;
   HM_CUDA(cudaGetLastError());
   return HM_OK;
