@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t bars = smem_base + kSmemBars;
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * BAR_COUNT);
-  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups]
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups] (lin8 tail) ...
+  float* bias_s = dot_scratch;                                                // ... and, before it, the current forward op's 512 biases
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
   const uint32_t rank = cluster_ctarank();                                    // 0 = leader (MMA issuer) of the pair
   const uint32_t lead_bars = mapa_rank(bars, 0);                              // the leader's barrier block (cluster address)
@@ -605,21 +606,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       // raw input x0 = [latent(32), xyz(3)] of this thread's point (deep_sdf_decoder.py:76-88)
       const int64_t lr = ok ? grow : (n_rows - 1);
       const int32_t li = (!P.rows && P.row_latent) ? __ldg(P.row_latent + lr) : 0;      // latent-table row of the point
-      auto x0 = [&](int k) -> float {
-        if (k >= HM_IN) return 0.f;
-        if (P.rows) return __ldg(P.rows + lr * HM_IN + k);
-        if (k < HM_LATENT) return __ldg(P.latents + (size_t)li * HM_LATENT + k);
-        if (P.grid_n > 0) return hm_grid_coord(lr, k - HM_LATENT, P.grid_n, P.grid_voxel, P.grid_radius);
-        return __ldg(P.xyz + lr * 3 + (k - HM_LATENT));
+      const float* lat_ptr = P.rows ? P.rows + lr * HM_IN : P.latents + (size_t)li * HM_LATENT;   // the 32 latent values are contiguous in both input modes
+      auto x0_xyz = [&](int c) -> float {      // xyz coordinate c of the point
+        if (P.rows) return __ldg(lat_ptr + HM_LATENT + c);
+        if (P.grid_n > 0) return hm_grid_coord(lr, c, P.grid_n, P.grid_voxel, P.grid_radius);
+        return __ldg(P.xyz + lr * 3 + c);
       };
       // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group g8 writes k in [8*g8, +8)
       {
         const float s0 = P.plan.ops[0].in_scale;
+        float xin[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 8 * g8 + 2 * e;
-          store_pair(smem, 0, p, k, x0(k) * s0, x0(k + 1) * s0, sat);
+        for (int i = 0; i < 8; ++i) xin[i] = 0.f;
+        if (g8 < 4) {                            // 8 independent loads: one memory latency, not eight
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xin[i] = __ldg(lat_ptr + 8 * g8 + i);
+        } else if (g8 == 4) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) xin[c] = x0_xyz(c);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) store_pair(smem, 0, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat);
         for (int j = 0; j < 4; ++j) publish(j);
       }
       float f_out = 0.f;
@@ -700,11 +707,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           const int col0 = col0_of(nh);
           if (kClass != 2 && opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
-            const float* bias = P.bias + opx * HM_HIDDEN + col0;
+            const float* bias = bias_s + col0;
             const float2 kk = make_float2(k_mul_x, k_mul_x);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * u)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * u + 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * u), b1 = *reinterpret_cast<const float4*>(bias + 8 * u + 4);
               float2 y0 = fma2(acc[nh][4 * u + 0], kk, make_float2(b0.x, b0.y)), y1 = fma2(acc[nh][4 * u + 1], kk, make_float2(b0.z, b0.w));
               float2 y2 = fma2(acc[nh][4 * u + 2], kk, make_float2(b1.x, b1.y)), y3 = fma2(acc[nh][4 * u + 3], kk, make_float2(b1.z, b1.w));
               const float y[8] = {y0.x, y0.y, y1.x, y1.y, y2.x, y2.y, y3.x, y3.y};
@@ -720,33 +727,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat, deep_sdf_decoder.py:87-88).
               // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the threads that
               // own columns >= 477 rewrite those units and clear their ReLU bits.
+              if (cq == 3) {                           // columns 480..511 = x0[3..34]: 29 latent values + xyz, loaded as one batch
+                float xv[32];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {            // static indices keep the accumulators in registers
-                if (cq == 2 && u < 3) continue;
+                for (int j = 0; j < 29; ++j) xv[j] = __ldg(lat_ptr + 3 + j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) xv[29 + c] = x0_xyz(c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float r[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) r[i] = xv[8 * u + i] * s_next_x;
+                  emit_unit(nh, u, r);
+                }
+                m_ = 0u;
+              } else {                                 // columns 448..479: 472..476 are the last lin3 outputs, 477..479 = x0[0..2]
                 float r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int j = 8 * u + i, col = col0 + j;
-                  if (col >= HM_SKIP_COL) {
-                    r[i] = x0(col - HM_SKIP_COL) * s_next_x;
-                    m_ &= ~(1u << j);
-                  } else {
-                    const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
-                    r[i] = fmaxf(fmaf(a, k_mul_x, __ldg(bias + j)), 0.f);
-                  }
+                for (int i = 0; i < 5; ++i) {
+                  const int j = 24 + i;
+                  const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
+                  r[i] = fmaxf(fmaf(a, k_mul_x, bias[j]), 0.f);
                 }
-                emit_unit(nh, u, r);
+#pragma unroll
+                for (int i = 5; i < 8; ++i) r[i] = __ldg(lat_ptr + (i - 5)) * s_next_x;
+                emit_unit(nh, 3, r);
+                m_ &= 0x1fffffffu;
               }
             }
             publish(2 * nh); publish(2 * nh + 1);
           } else if (kClass != 1 && opx == 7) {
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
-            const float* bias = P.bias + 7 * HM_HIDDEN + col0;
+            const float* bias = bias_s + col0;
             const float* w8 = P.w8 + col0;
             const float2 uu = make_float2(unscale_x, unscale_x);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float2 bz = __ldg(reinterpret_cast<const float2*>(bias + 2 * i));
+              const float2 bz = *reinterpret_cast<const float2*>(bias + 2 * i);
               const float2 wz = __ldg(reinterpret_cast<const float2*>(w8 + 2 * i));
               const float2 y = fma2(acc[nh][i], uu, bz);
               m_ |= ((y.x > 0.f) ? 1u : 0u) << (2 * i) | ((y.y > 0.f) ? 1u : 0u) << (2 * i + 1);
@@ -797,6 +814,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           finalize(I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pm1);
           if (kJac && op - 1 < 7) my_masks[(size_t)(op - 1) * kMaskStride + 1] = pm1;
         }
+        if (op <= 7) {
+          // stage this op's biases in shared memory (L1 is ~0 KB next to 226 KB of shared memory: a global load in the finalize
+          // loop is an exposed L2 round trip); the previous op's are dead once its deferred half is done
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          bias_s[e_w * 32 + lane] = __ldg(P.bias + op * HM_HIDDEN + e_w * 32 + lane);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        }
         if (narrow) {
 #pragma unroll 1
           for (int st = 0; st < 3; ++st) promote(I0, I0);
@@ -812,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           if (!defer) finalize(I1, I2, op, k_mul, unscale, s_next, m1);
         }
         if (op == 7) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
           dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           const float b8 = __ldg(P.b8);
