@@ -630,12 +630,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         for (int j = 0; j < 4; ++j) publish(j);
       }
       float f_out = 0.f;
-      // Accumulators of this thread: acc[nh][i] = columns col0_of(nh) + 2i + {0, 1}.  They and the ReLU bits live across op
-      // boundaries: output half 1 of an op is finalized only after the first partial of the NEXT op has been collected
-      // (schedule below), so that the tensor core never waits for it.
+      // Accumulators of this thread: acc[nh][i] = columns col0_of(nh) + 2i + {0, 1}.
       float2 acc[2][16];
       uint32_t m0 = 0u, m1 = 0u;             // ReLU bits of the current op: output half 0 / half 1, bit j = column col0 + j
-      uint32_t pm1 = 0u;                     // half-1 bits of the previous op (for its deferred half)
       float dot = 0.f;
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
@@ -648,9 +645,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const float k_mul = unscale * s_next;
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns (32 TMEM columns), one group per step
         const bool wide = (o.n_kchunks != 1);
-        const bool has_pending = (op != 0 && op != 8);   // the previous op left its output half 1 to this one
-        const bool defer = (op != 7 && op != 15);        // ... and this op leaves its own to the next
-        pm1 = m1;
         m0 = m1 = 0u;
         if (kJac && op >= 8 && op < 15) {
           const uint2 mw = *reinterpret_cast<const uint2*>(my_masks + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
@@ -697,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           if (e_w == 0 && lane == 0) trace(1 + rank, 12, op, gseq & 0xffff);
         };
         // Turn the finished output half nh of op `opx` into the next op's A chunks 4*nh .. 4*nh+3 (k-steps 2*nh, 2*nh+1) or the
-        // final outputs.  kClass: 0 = any op, 1 = opx is a hidden layer (forward or backward: the deferred half), 2 = lin7.
+        // final outputs.  kClass: 0 = any op (1 / 2 restrict the compiled branches to hidden layers / lin7).
         auto finalize = [&](auto NH, auto CLASS, const int opx, const float k_mul_x, const float unscale_x, const float s_next_x, uint32_t& m_) {
           constexpr int nh = decltype(NH)::value, kClass = decltype(CLASS)::value;
 #ifdef HM_TC_COUNTERS
@@ -804,36 +798,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           if (e_w == 0 && lane == 0) trace(1 + rank, 14, opx, nh);
         };
         // ---- Schedule of one op (groups in the issue order of group_of(); P = promote, F(nh) = finalize an output half):
-        //        P(0,0) [F'(1) of the previous op] P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0) P(2,1) P(3,1)   [F(1) -> next op]
-        //      Output half 0 is complete two groups before the op ends and is turned into the next op's A chunks 0..3 while
-        //      the tensor core still works on half 1; half 1 is finalized under the next op's first groups (which read
-        //      chunks 0..3 only).
-        promote(I0, I1);
-        if (has_pending) {
-          const float q_unscale = P.plan.ops[op - 1].out_unscale;
-          finalize(I1, I1, op - 1, q_unscale * o.in_scale, q_unscale, o.in_scale, pm1);
-          if (kJac && op - 1 < 7) my_masks[(size_t)(op - 1) * kMaskStride + 1] = pm1;
-        }
+        //        P(0,0) P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0) P(2,1) P(3,1) F(1)
+        //      Output half 0 is complete two groups before the op ends and is turned into the next op's A chunks 0..3 while the
+        //      tensor core still works on half 1; F(1) runs under the next op's first four groups (they read chunks 0..3 only) --
+        //      with four TMEM buffers the tensor core can be that far ahead of the promotions.
         if (op <= 7) {
           // stage this op's biases in shared memory (L1 is ~0 KB next to 226 KB of shared memory: a global load in the finalize
-          // loop is an exposed L2 round trip); the previous op's are dead once its deferred half is done
+          // loop is an exposed L2 round trip)
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           bias_s[e_w * 32 + lane] = __ldg(P.bias + op * HM_HIDDEN + e_w * 32 + lane);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
+        promote(I0, I1);
         if (narrow) {
 #pragma unroll 1
           for (int st = 0; st < 3; ++st) promote(I0, I0);
         } else {
-          if (wide) {
-            promote(I1, I1); promote(I0, I0); promote(I1, I0); promote(I0, I0); promote(I0, I0);
-          } else {
-            promote(I1, I1);       // F0: both output halves read A chunk 0 -- collect both before it is overwritten
-          }
+          promote(I1, I1);
+          if (wide) { promote(I0, I0); promote(I1, I0); promote(I0, I0); promote(I0, I0); }
           finalize(I0, I0, op, k_mul, unscale, s_next, m0);
-          if (kJac && op < 7) my_masks[(size_t)op * kMaskStride] = m0;
           if (wide) { promote(I1, I0); promote(I1, I0); }
-          if (!defer) finalize(I1, I2, op, k_mul, unscale, s_next, m1);
+          finalize(I1, I0, op, k_mul, unscale, s_next, m1);
+          if (kJac && op < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)op * kMaskStride) = make_uint2(m0, m1);
         }
         if (op == 7) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
