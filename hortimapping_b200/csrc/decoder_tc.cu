@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   if (threadIdx.x == 0) {
     // W_FULL of the leader also collects the peer's "my half has landed" arrive
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), rank == 0 ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
-    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG);
+    for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG / 2);      // a k-step's chunks come from half of the warps
     for (int b = 0; b < kBufs; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) store_pair(smem, 0, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat);
-        for (int j = 0; j < 4; ++j) publish(j);
+        publish(cq >> 1);                        // every warp arrives once per k-step of its own chunks' parity (see finalize)
+        publish(2 + (cq >> 1));
       }
       float f_out = 0.f;
       // Accumulators of this thread: acc[nh][i] = columns col0_of(nh) + 2i + {0, 1}.
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
             const float* bias = bias_s + col0;
             const float2 kk = make_float2(k_mul_x, k_mul_x);
+            if (nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");      // k-step 0 first (see below)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * u), b1 = *reinterpret_cast<const float4*>(bias + 8 * u + 4);
@@ -749,7 +751,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 m_ &= 0x1fffffffu;
               }
             }
-            publish(2 * nh); publish(2 * nh + 1);
+            // Warps cq = 0,1 own the chunks of k-step 2*nh, warps cq = 2,3 those of k-step 2*nh + 1.  For output half 0 the
+            // second pair waits for the first: the next op's first group needs k-step 0 only, and two warps per scheduler
+            // deliver it in half the time four would need for both steps.
+            publish(2 * nh + (cq >> 1));
+            if (nh == 0 && cq < 2) asm volatile("bar.arrive 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
           } else if (kClass != 1 && opx == 7) {
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108)
             const float* bias = bias_s + col0;
@@ -766,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             }
           } else if (kClass != 2 && opx > 7 && opx < 15) {
             // ---------------- backward through lin_l (l = 15 - opx = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
+            if (nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float r[8];
@@ -790,7 +797,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               }
               __threadfence_block();
             }
-            publish(2 * nh); publish(2 * nh + 1);
+            publish(2 * nh + (cq >> 1));
+            if (nh == 0 && cq < 2) asm volatile("bar.arrive 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
           }
 #ifdef HM_TC_COUNTERS
           t_fin += clock64() - tf0;
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 for (int i = 0; i < 8; ++i) r[i] = ((m_ >> (8 * u + i)) & 1u) ? c7 * w[i] : 0.f;
                 emit_unit(nh, u, r);
               }
-              publish(2 * nh); publish(2 * nh + 1);
+              publish(2 * nh + (cq >> 1));
             }
           }
         } else if (op == 15) {
