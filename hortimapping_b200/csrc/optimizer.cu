@@ -537,7 +537,9 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
   __shared__ int s_n[3];
   const int b0 = a.fruit_block_begin[f], b1 = a.fruit_block_begin[f + 1];
   // fixed-order sum of the block partials per term
-  for (int e = threadIdx.x; e < 3 * (tri + est); e += 64) {
+  // (the latent-only loop has the recon term only: its blocks all carry term 2)
+  const int term_lo = a.joint ? 0 : 2;
+  for (int e = threadIdx.x + term_lo * (tri + est); e < 3 * (tri + est); e += 64) {
     const int term = e / (tri + est), idx = e % (tri + est);
     double acc = 0.0;
     for (int b = b0; b < b1; ++b)
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
   const double wd = a.joint ? P.w_depth / (double)n_d : 0.0, wm = a.joint ? P.w_mask / (double)n_d : 0.0, wr = P.w_recon / (double)n_r;
   float* lat = a.latents + (size_t)f * HM_LATENT;
   for (int e = threadIdx.x; e < tri + est; e += 64) {
-    double v = wd * sAcc[0][e] + wm * sAcc[1][e] + wr * sAcc[2][e];
+    double v = a.joint ? wd * sAcc[0][e] + wm * sAcc[1][e] + wr * sAcc[2][e] : wr * sAcc[2][e];   // (terms 0, 1 are not summed when !joint)
     if (e < tri) {
       int r = 0, rem = e;
       while (rem >= est - r) { rem -= est - r; ++r; }
@@ -603,12 +605,22 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
   // Gaussian elimination with partial pivoting on [H | b] (delta_x = H^-1 b, :234)
   for (int k = 0; k < est; ++k) {
     __shared__ int s_piv;
-    if (threadIdx.x == 0) {
-      int p = k;
-      double best = fabs(sH[k][k]);
-      for (int i = k + 1; i < est; ++i)
-        if (fabs(sH[i][k]) > best) { best = fabs(sH[i][k]); p = i; }
-      s_piv = p;
+    if (threadIdx.x < 32) {
+      // arg max_i |H[i][k]|, i >= k, the FIRST maximum on ties (what a serial scan with '>' finds): lanes cover rows
+      // i = k + lane and k + lane + 32 (est <= 39), then a shuffle reduction on (value, index)
+      double best = -1.0;
+      int p = est;
+      for (int i = k + (int)threadIdx.x; i < est; i += 32) {
+        const double v = fabs(sH[i][k]);
+        if (v > best) { best = v; p = i; }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int op = __shfl_xor_sync(0xffffffffu, p, off);
+        if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+      }
+      if (threadIdx.x == 0) s_piv = p;
     }
     __syncthreads();
     const int p = s_piv;
@@ -622,12 +634,14 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
     }
     __syncthreads();
   }
+  // back substitution, column oriented: once dx[i] is known every row above it subtracts its term (one row per thread)
+  for (int i = est - 1; i >= 0; --i) {
+    if (threadIdx.x == 0) s_dx[i] = sH[i][est] / sH[i][i];
+    __syncthreads();
+    if ((int)threadIdx.x < i) sH[threadIdx.x][est] -= sH[threadIdx.x][i] * s_dx[i];
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    for (int i = est - 1; i >= 0; --i) {
-      double s = sH[i][est];
-      for (int c = i + 1; c < est; ++c) s -= sH[i][c] * s_dx[c];
-      s_dx[i] = s / sH[i][i];
-    }
     float dx[kE];
     for (int i = 0; i < est; ++i) dx[i] = (float)s_dx[i];
     if (a.last_dx) for (int i = 0; i < est; ++i) a.last_dx[(size_t)f * kE + i] = dx[i];
