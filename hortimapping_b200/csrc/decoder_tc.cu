@@ -73,7 +73,6 @@ struct TcParams {
   uint32_t* trace;            // debug timeline of CTA 0 / 1 (hm_debug_tc_trace) or null
   int32_t grid_n;             // > 0: xyz of row i = voxel grid point i (fused mesher grid, hm_rows)
   float grid_voxel, grid_radius;
-  float b0_in_scale_dummy;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -257,37 +256,7 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-// TMEM -> registers, 16 lanes x 256 bit x 4 repeats (= 32 accumulator columns of 16 rows): thread t receives,
-// per 8-column block e, v[4e+0..1] = (row t/4, columns 8e + 2(t%4) + {0,1}) and v[4e+2..3] = the same columns of
-// row t/4 + 8 (cute SM100_TMEM_LOAD_16dp256b4x: the mma.sync C-fragment layout).
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait for all outstanding TMEM loads; the loaded registers pass through the statement so that no consumer of `a` / `b`
-// can be scheduled above the wait (the arithmetic below is non-volatile asm and would otherwise be free to move)
-__device__ __forceinline__ void tmem_ld_wait_dep(float2 (&a)[8], float2 (&b)[8]) {
-  uint32_t* x = reinterpret_cast<uint32_t*>(a);
-  uint32_t* y = reinterpret_cast<uint32_t*>(b);
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(x[8]), "+r"(x[9]),
-                 "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15])
-               :
-               : "memory");
-  asm volatile(""
-               : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]), "+r"(y[8]), "+r"(y[9]),
-                 "+r"(y[10]), "+r"(y[11]), "+r"(y[12]), "+r"(y[13]), "+r"(y[14]), "+r"(y[15])
-               :
-               : "memory");
-}
-
 // packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100) and saturating fp16x2 pack
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   unsigned long long r;
@@ -637,7 +606,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       float dot = 0.f;
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
-      const std::integral_constant<int, 2> I2{};
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op, ++op_seq) {
         const hm_tc_op& o = P.plan.ops[op];
@@ -1217,7 +1185,6 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.grid_n = rows.grid_n;
   P.grid_voxel = rows.grid_voxel;
   P.grid_radius = rows.grid_radius;
-  P.b0_in_scale_dummy = 0.f;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
   const int csize = 2;                                              // the kernel is a CTA-pair kernel
   const int64_t n_units = (n_tiles + csize - 1) / csize;             // a unit = one 64-row tile per CTA of the cluster
