@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128) normal_eq_kernel(const RedBlock* __restri
                                                         const float* __restrict__ J_d, const float* __restrict__ J_m,
                                                         const float* __restrict__ res_d, const float* __restrict__ res_m,
                                                         const int32_t* __restrict__ ray_k, const float* __restrict__ J_r,
-                                                        const float* __restrict__ res_r, const uint8_t* __restrict__ active,
+                                                        const float* __restrict__ res_r, int r_stride, const uint8_t* __restrict__ active,
                                                         float* __restrict__ partials, int32_t* __restrict__ block_items) {
   __shared__ float sJ[kRedItems][kE + 1];
   __shared__ float sW[kRedItems], sR[kRedItems];
@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(128) normal_eq_kernel(const RedBlock* __restri
         if (robust && B.term == 2) w = huber_w2(rr, P.t_recon);      // :183-187
         atomicAdd(&s_cnt, 1);
       }
-      for (int c = 0; c < est; ++c) sJ[t][c] = ok ? J[it * kE + c] : 0.f;
+      const int stride = (B.term == 2) ? r_stride : kE;      // the latent-only loop reads the decoder's Jacobian rows in place
+      for (int c = 0; c < est; ++c) sJ[t][c] = ok ? J[it * stride + c] : 0.f;
     } else {
       for (int c = 0; c < est; ++c) sJ[t][c] = 0.f;
     }
@@ -877,12 +878,20 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
       ray_jacobian_kernel<<<nblk(n_rays, 128), 128, 0, st>>>(n_rays, M, pose_dim, w.ray_mask, w.ray_slot, w.coef_e, w.coef_m, w.xyz_g, w.jac_g, w.J_d, w.J_m);
       ++launches;
     }
-    point_jacobian_kernel<<<nblk(n_points, 128), 128, 0, st>>>(n_points, pose_dim, w.xyz_g, w.sdf_g, w.jac_g, w.res_r, w.J_r);
-    normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.J_r, w.res_r, w.active,
-                                               w.partials, w.block_items);
+    if (joint) {
+      point_jacobian_kernel<<<nblk(n_points, 128), 128, 0, st>>>(n_points, pose_dim, w.xyz_g, w.sdf_g, w.jac_g, w.res_r, w.J_r);
+      normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.J_r, w.res_r, kE, w.active,
+                                                 w.partials, w.block_items);
+      ++launches;
+    } else {
+      // latent only (optimizer.py:306-429): J = d sdf / d latent = the first 32 columns of the decoder's Jacobian rows and the
+      // residual is the SDF itself (loss.py:219-243 with the pose fixed) -- read both where the decoder wrote them
+      normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.jac_g, w.sdf_g, HM_IN, w.active,
+                                                 w.partials, w.block_items);
+    }
     sa.iter = it;
     solve_kernel<<<nf, 64, 0, st>>>(sa, P);
-    launches += 4;
+    launches += 3;
   }
   HM_CUDA(cudaGetLastError());
   ctx->counters.kernel_launches += launches;
