@@ -537,20 +537,35 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
   __shared__ double s_dx[kE];
   __shared__ int s_n[3];
   const int b0 = a.fruit_block_begin[f], b1 = a.fruit_block_begin[f + 1];
-  // fixed-order sum of the block partials per term
-  // (the latent-only loop has the recon term only: its blocks all carry term 2)
+  // The blocks of a fruit are sorted by term: find the three ranges once, so that the sums below are plain loops whose loads
+  // are independent of each other (a term test per block made every load wait for the previous one).
+  __shared__ int s_tb[4];                // blocks [s_tb[t], s_tb[t + 1]) carry term t
+  if (threadIdx.x < 4) s_tb[threadIdx.x] = (threadIdx.x == 0) ? b0 : b1;
+  __syncthreads();
+  for (int b = b0 + 1 + (int)threadIdx.x; b < b1; b += 64) {
+    const int t0 = a.blocks[b - 1].term, t1 = a.blocks[b].term;
+    for (int t = t0 + 1; t <= t1; ++t) s_tb[t] = b;          // first block of term t (and of any empty term before it)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && b1 > b0) {                          // terms missing at the front / back of the range
+    const int first = a.blocks[b0].term, last = a.blocks[b1 - 1].term;
+    for (int t = 1; t <= first; ++t) s_tb[t] = b0;
+    for (int t = last + 1; t < 3; ++t) s_tb[t] = b1;
+  }
+  __syncthreads();
+  // fixed-order sum of the block partials per term (the latent-only loop has the recon term only)
   const int term_lo = a.joint ? 0 : 2;
   for (int e = threadIdx.x + term_lo * (tri + est); e < 3 * (tri + est); e += 64) {
     const int term = e / (tri + est), idx = e % (tri + est);
+    const int tb0 = s_tb[term], tb1 = s_tb[term + 1];
     double acc = 0.0;
-    for (int b = b0; b < b1; ++b)
-      if (a.blocks[b].term == term) acc += (double)a.partials[(size_t)b * kPartial + idx];
+#pragma unroll 4
+    for (int b = tb0; b < tb1; ++b) acc += (double)a.partials[(size_t)b * kPartial + idx];
     sAcc[term][idx] = acc;
   }
   if (threadIdx.x < 3) {
     int n = 0;
-    for (int b = b0; b < b1; ++b)
-      if (a.blocks[b].term == threadIdx.x) n += a.block_items[b];
+    for (int b = s_tb[threadIdx.x]; b < s_tb[threadIdx.x + 1]; ++b) n += a.block_items[b];
     s_n[threadIdx.x] = n;
   }
   __syncthreads();
