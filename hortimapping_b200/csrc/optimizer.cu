@@ -532,7 +532,8 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
   const int est = a.joint ? P.est : HM_LATENT;
   const int pd = a.joint ? P.pose_dim : 0;
   const int tri = est * (est + 1) / 2;
-  __shared__ double sH[kE][kE + 1];      // augmented [H | b]
+  __shared__ double sH[kE][kE + 2];      // augmented [H | b]; the row stride of 41 doubles keeps the per-row accesses of the
+                                         // elimination (one row per thread) off the same banks (40 would be a 16-way conflict)
   __shared__ double sAcc[3][kPartial];
   __shared__ double s_dx[kE];
   __shared__ int s_n[3];
