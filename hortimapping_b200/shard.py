@@ -40,3 +40,27 @@ def gather_records(local: torch.Tensor, n_total: int) -> torch.Tensor:
     out = torch.empty(world * mx, RECORD, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad)
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def optimize_sharded(opt, latents: torch.Tensor, T_ow: torch.Tensor, points_w, render_datas=None, cube_radius=0.08, pose_known=False):
+    """Sequence-level driver (host side): every rank holds the same list of fruits, optimises only its own
+    contiguous block with ONE batched call (`Optimizer.shape_pose_joint_opt_batch`, or `shape_opt_deepsdf_batch` when
+    `render_datas` is None) and ONE all-gather brings every fruit's (latent, T_ow, iter_count) to every rank, in fruit order.
+    Fruits are independent, so the result is bit-identical to a single-rank call on the whole list."""
+    n = latents.shape[0]
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(n, rank, world)
+    lat, T = latents[lo:hi].clone(), T_ow[lo:hi].clone()
+    if hi > lo:
+        if render_datas is None:
+            lat, T, iters, _ = opt.shape_opt_deepsdf_batch(lat, T, list(points_w[lo:hi]))
+        else:
+            import numpy as np
+            cr = np.broadcast_to(np.asarray(cube_radius, np.float32), (n,))[lo:hi]
+            pk = np.broadcast_to(np.asarray(pose_known, bool), (n,))[lo:hi]
+            lat, T, iters, _ = opt.shape_pose_joint_opt_batch(lat, T, list(render_datas[lo:hi]), list(points_w[lo:hi]), cr, pk)
+    else:
+        iters = torch.zeros(0, dtype=torch.int32, device=latents.device)
+    rec = gather_records(pack_records(lat, T, iters), n)
+    return unpack_records(rec)
