@@ -162,6 +162,19 @@ extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
   return HM_OK;
 }
 
+extern "C" int hm_saturation_count(hm_context* ctx, int64_t* h_count) {
+  HM_CHECK(ctx && h_count, "hm_saturation_count: null argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  *h_count = 0;
+  if (!ctx->d_tc_flags) return HM_OK;
+  int32_t v = 0;
+  HM_CUDA(cudaDeviceSynchronize());
+  HM_CUDA(cudaMemcpy(&v, ctx->d_tc_flags, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t)));
+  *h_count = v;
+  return HM_OK;
+}
+
 extern "C" int hm_profile_enable(hm_context* ctx, int on) {
   HM_CHECK(ctx, "hm_profile_enable: null context");
   ctx->profiling = on ? 1 : 0;

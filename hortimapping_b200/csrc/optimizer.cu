@@ -703,6 +703,17 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
 }
 
 
+// The tensor-core decoder counts the launches in which an fp16 operand conversion saturated (flags[0]).  After the loop that
+// count is turned into HM_STATUS_F16_SATURATED on every fruit of the batch (the fruit cannot be attributed) and reset.
+__global__ void saturation_status_kernel(int32_t* __restrict__ flags, int n_fruits, int32_t* __restrict__ status) {
+  const int sat = flags[0];
+  __syncthreads();
+  if (sat != 0)
+    for (int f = threadIdx.x; f < n_fruits; f += blockDim.x) atomicOr(&status[f], HM_STATUS_F16_SATURATED);
+  __syncthreads();
+  if (threadIdx.x == 0) flags[0] = 0;
+}
+
 // host helpers ---------------------------------------------------------------------------------
 DevParams make_dev_params(const hm_opt_params* p, bool joint) {
   DevParams d;
@@ -908,6 +919,10 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
     sa.iter = it;
     solve_kernel<<<nf, 64, 0, st>>>(sa, P);
     launches += 3;
+  }
+  if (ctx->engine == HM_ENGINE_TC && ctx->d_tc_flags) {
+    saturation_status_kernel<<<1, 256, 0, st>>>(ctx->d_tc_flags, nf, b->d_status);
+    ++launches;
   }
   HM_CUDA(cudaGetLastError());
   ctx->counters.kernel_launches += launches;

@@ -119,6 +119,13 @@ class Decoder:
     def profile(self, on: bool):
         check(self._L.hm_profile_enable(self._h, int(bool(on))), "hm_profile_enable")
 
+    def saturation_count(self) -> int:
+        """Thread blocks of the tensor-core engine, since the last call, in which an operand left the calibrated fp16 range
+        (hm_saturation_count; synchronises).  Non-zero means the results were not fp32-grade: calibrate() on representative rows."""
+        n = C.c_int64(0)
+        check(self._L.hm_saturation_count(self._h, C.byref(n)), "hm_saturation_count")
+        return int(n.value)
+
     def counters(self) -> dict:
         c = _lib.Counters()
         check(self._L.hm_get_counters(self._h, C.byref(c)), "hm_get_counters")

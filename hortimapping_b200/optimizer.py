@@ -130,6 +130,10 @@ class Optimizer(object):
         return iters, status
 
     def _report(self, status: np.ndarray):
+        if any(int(s) & _lib.STATUS.get("F16_SATURATED", 0x40) for s in status):
+            import warnings
+            warnings.warn("hortimapping_b200: an operand left the calibrated fp16 range of the tensor-core decoder "
+                          "(HM_STATUS_F16_SATURATED): results are not fp32-grade, call Decoder.calibrate() on representative rows")
         for f, s in enumerate(status):
             if s & _lib.STATUS["FRAME_SKIPPED"]:
                 print("This frame is not valid")                       # optimizer.py:131

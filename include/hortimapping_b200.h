@@ -135,6 +135,10 @@ int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
 /* Counters are cumulative since hm_create.  With profiling enabled every decoder kernel launch is bracketed
  * by CUDA events on its stream; hm_get_counters then waits for the recorded events and adds their durations. */
 int hm_get_counters(hm_context* ctx, hm_counters* out);
+/* Number of thread blocks of the tensor-core decoder, since the last call, in which an operand left the calibrated fp16 range
+ * (the conversion saturates, the result is then NOT fp32-grade: re-run hm_calibrate on representative rows).  Synchronises the
+ * device and resets the count.  The optimisers report the same condition per call as HM_STATUS_F16_SATURATED. */
+int hm_saturation_count(hm_context* ctx, int64_t* h_count);
 int hm_profile_enable(hm_context* ctx, int on);
 
 /* wild_completion/utils.py:144-172 decode_sdf: sdf[i] = f(latent, xyz[i]). */

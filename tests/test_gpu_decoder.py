@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import hm_oracle as O
-from tests.helpers import load_npz, oracle_decoder
+from tests.helpers import cfg_of, load_npz, oracle_decoder
 
 pytestmark = pytest.mark.gpu
 
@@ -173,3 +173,47 @@ def test_tc_and_simt_engines_agree_on_a_large_batch():
     perm = torch.randperm(n, device="cuda")
     y_p, _ = dec._eval_rows(t[perm], with_jac=False)
     assert torch.equal(y_p, y_tc[perm]), "a row's SDF must not depend on its tile neighbours"
+
+
+def test_fp16_saturation_is_reported_not_silent():
+    """The tensor-core engine scales operands into the fp16 range with calibrated powers of two (64x headroom).  Rows far
+    outside the calibration set saturate the conversion: the library must say so (hm_saturation_count, HM_STATUS_F16_SATURATED)
+    instead of returning silently degraded values, and a calibration on representative rows must clear the condition."""
+    import warnings
+    from hortimapping_b200 import _lib
+    from hortimapping_b200.decoder import Decoder
+    from hortimapping_b200.optimizer import Optimizer
+    from tests.helpers import random_decoder_weights
+    W, b = random_decoder_weights(5)
+    dec = Decoder(W, b)
+    g = np.random.default_rng(2)
+    small = np.concatenate([g.normal(0, 0.01, (4096, 32)), (g.random((4096, 3)) * 2 - 1) * 1e-3], 1).astype(np.float32)
+    big = np.concatenate([g.normal(0, 0.1, (4096, 32)), (g.random((4096, 3)) * 2 - 1) * 5.0], 1).astype(np.float32)
+    dec.calibrate(torch.from_numpy(small))
+    dec.saturation_count()
+    dec._eval_rows(torch.from_numpy(small).cuda(), with_jac=True)
+    assert dec.saturation_count() == 0
+    dec._eval_rows(torch.from_numpy(big).cuda(), with_jac=True)
+    assert dec.saturation_count() > 0
+    assert dec.saturation_count() == 0                                   # reading resets
+    cfg = cfg_of(load_npz("fruit_wild"))
+    cfg["device"] = "cuda"
+    cfg["opt"]["converge"]["max_iter"] = 2
+    opt = Optimizer(cfg, dec, None, None)
+    lat = torch.zeros(2, 32, device="cuda")
+    T = torch.eye(4, device="cuda").repeat(2, 1, 1)
+    pts = [big[:300, 32:], big[300:700, 32:]]
+    _, _, _, st = opt.shape_opt_deepsdf_batch(lat, T, pts)
+    assert all(int(s) & _lib.STATUS["F16_SATURATED"] for s in st.cpu().tolist())
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        opt._report(st.cpu().numpy())
+    assert any("F16_SATURATED" in str(w.message) for w in wlist)
+    # calibrated on rows that represent what is evaluated: clean again, and fp32-grade
+    from tests.gpu_helpers import random_rows
+    mid, mid_cal = random_rows(4096, seed=5), random_rows(4096, seed=6)
+    dec.calibrate(torch.from_numpy(mid_cal))
+    y, _ = dec._eval_rows(torch.from_numpy(mid).cuda(), with_jac=False)
+    assert dec.saturation_count() == 0
+    y_ref = O.DecoderOracle(W, b, (4,), np.float64).forward(mid.astype(np.float64))
+    np.testing.assert_allclose(y.cpu().numpy().reshape(-1), y_ref.reshape(-1), rtol=1e-4, atol=2e-6)
