@@ -84,7 +84,8 @@ def test_force_key_error_dict_and_dropin_module_paths():
         d.missing
     from hortimapping_b200 import dropin
     saved = {k: sys.modules.get(k) for k in ("wild_completion", "wild_completion.optimizer", "wild_completion.mesher",
-                                            "wild_completion.loss", "deepsdf", "deepsdf.deep_sdf", "deepsdf.deep_sdf.workspace")}
+                                            "wild_completion.loss", "deepsdf", "deepsdf.deep_sdf", "deepsdf.deep_sdf.workspace",
+                                            "metrics_3d", "metrics_3d.chamfer_distance", "metrics_3d.precision_recall")}
     try:
         dropin.install(None)
         from wild_completion.optimizer import Optimizer
@@ -92,6 +93,10 @@ def test_force_key_error_dict_and_dropin_module_paths():
         from deepsdf.deep_sdf.workspace import config_decoder, load_latent_vectors
         import hortimapping_b200.optimizer as ho
         assert Optimizer is ho.Optimizer and callable(config_decoder) and callable(load_latent_vectors) and MeshExtractor
+        from metrics_3d.chamfer_distance import ChamferDistance            # run_shape_completion_challenge.py:15-16
+        from metrics_3d.precision_recall import PrecisionRecall
+        import hortimapping_b200.metrics as hmx
+        assert ChamferDistance is hmx.ChamferDistance and PrecisionRecall is hmx.PrecisionRecall
     finally:
         for k, v in saved.items():
             if v is None:
@@ -118,3 +123,33 @@ def test_shard_ranges_cover_everything():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_metric_input_conversion_and_bookkeeping_without_gpu():
+    """metrics_3d/metric.py:15-58 input handling and the reference's bookkeeping for empty predictions (no device call)."""
+    from hortimapping_b200.metrics import ChamferDistance, Metrics3D, PrecisionRecall, _points
+
+    class Pcd:                      # duck-typed open3d.geometry.PointCloud
+        def __init__(self, p):
+            self.points = p
+
+    class Mesh:                     # duck-typed open3d.geometry.TriangleMesh: sampled with ITS OWN sample_points_uniformly
+        vertices = [0, 1, 2]
+
+        def sample_points_uniformly(self, n):
+            assert n == 1000000     # metric.py:43
+            return Pcd(np.ones((5, 3)))
+
+    a = np.arange(12, dtype=np.float32).reshape(4, 3)
+    assert _points(np.concatenate([a, a], 1)).shape == (4, 3) and _points(a).dtype == np.float64
+    np.testing.assert_array_equal(_points(torch.from_numpy(a)), a.astype(np.float64))
+    np.testing.assert_array_equal(_points(Pcd(a.tolist())), a.astype(np.float64))
+    assert _points(Mesh()).shape == (5, 3)
+    m = Metrics3D()
+    assert m.prediction_is_empty(np.zeros((0, 3))) and not m.prediction_is_empty(a)
+    assert m.prediction_is_empty(Pcd([])) and not m.prediction_is_empty(Mesh())
+    cd, pr = ChamferDistance(), PrecisionRecall(0.001, 0.01, 10)
+    cd.update(a, np.zeros((0, 3)))                                   # chamfer_distance.py:17-19
+    pr.update(a, torch.zeros(0, 3))                                  # precision_recall.py:20-25
+    assert cd.compute() == 0 and pr.compute_at_threshold(0.005)[:3] == (0, 0, 0)
+    assert pr.find_nearest_threshold(0.0049) == pr.thresholds[4]
