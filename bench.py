@@ -295,13 +295,14 @@ def main():
     except Exception:
         pass
     achieved = flop_per_launch / (dec_ms / max(n_launch, 1) * 1e-3) / 1e12 if n_launch else None
-    traffic = None
+    traffic, tensor_pct = None, None
     tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tfile):
-        traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        tj = json.load(open(tfile))
+        traffic, tensor_pct = tj.get("dram_bytes_per_launch"), tj.get("tensor_pipe_active_pct")
     roofline = {"bound": "tensor", "kernel": "tc_decoder_kernel<true> (fused DeepSDF forward + input gradient)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_flop_per_launch": flop_per_launch,
+                "traffic": traffic, "tensor_pipe_active_pct_ncu": tensor_pct, "peak_source": peak_src, "algorithmic_flop_per_launch": flop_per_launch,
                 "issued_mma_flop_per_launch": 3 * flop_per_launch, "launches": n_launch, "avg_launch_ms": dec_ms / max(n_launch, 1),
                 "kernel_share_of_step": dec_ms / total_ms}
 

@@ -60,8 +60,11 @@ if os.path.exists(rep):
     i_w = [i for i, h in enumerate(hdr) if h == "dram__bytes_write.sum"][0]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tr = [float(r[i_r]) * scale[units[i_r]] + float(r[i_w]) * scale[units[i_w]] for r in rows[2:]]
-    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag}_ncu_decoder.txt",
-               "kernel": rows[2][hdr.index("Kernel Name")]}, open(os.path.join(PROF, "dominant_kernel_traffic.json"), "w"))
+    i_t = [i for i, h in enumerate(hdr) if h == "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
+    tp = [float(r[i_t[0]]) for r in rows[2:]] if i_t else []
+    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "tensor_pipe_active_pct": (sum(tp) / len(tp)) if tp else None,
+               "source": f"profiles/{tag}_ncu_decoder.txt", "kernel": rows[2][hdr.index("Kernel Name")]},
+              open(os.path.join(PROF, "dominant_kernel_traffic.json"), "w"))
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     tmp = os.path.join(OUT, "source.csv")
     open(tmp, "w").write(src)
