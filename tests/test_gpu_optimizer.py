@@ -220,3 +220,41 @@ def test_invalid_submap_keeps_state():
     np.testing.assert_array_equal(lat[0].cpu().numpy(), c["init_latent"])
     np.testing.assert_array_equal(T[0].cpu().numpy(), c["init_T_ow"])
     assert not np.array_equal(lat[1].cpu().numpy(), c["init_latent"])
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] at full size (64 fruits x 2048 points), a few iterations, through size-independent properties:
+    every fruit of the batch gets bit-identically what a single-fruit call gives it (fruits are independent; several waves
+    of the persistent decoder grid, ragged tile assignment), permuting the fruits permutes the result, the weighted SDF
+    objective the loop minimises does not increase, and the device loop agrees with the fp64 oracle for a sampled fruit."""
+    from hortimapping_b200 import synth
+    c = load_npz("fruit_wild")
+    cfg = zero_eps(cfg_of(c), 4)
+    opt, dec = make_opt(cfg)
+    _, _, codes = __import__("tests.helpers", fromlist=["pepper_weights"]).pepper_weights()
+    n_f, n_p = 64, 2048
+    g = np.random.default_rng(21)
+    # surface-like points: mean-shape level set points jittered, one cloud per fruit
+    base = ((g.random((n_f, n_p, 3)) * 2 - 1) * 0.045).astype(np.float32)
+    lat0 = (codes.mean(0)[None, :] + 0.02 * g.standard_normal((n_f, 32))).astype(np.float32)
+    pts = [base[i] for i in range(n_f)]
+    T0 = torch.eye(4).repeat(n_f, 1, 1).cuda()
+    lat = torch.from_numpy(lat0).cuda()
+    lat_b, _, iters, status = opt.shape_opt_deepsdf_batch(lat.clone(), T0.clone(), pts)
+    assert iters.cpu().tolist() == [4] * n_f and all(int(s) == 0x8 for s in status.cpu().tolist())
+    for f in (0, 17, 63):                                             # batch == single, bit for bit
+        l1, _, _, _ = opt.shape_opt_deepsdf_batch(lat[f:f + 1].clone(), T0[f:f + 1].clone(), [pts[f]])
+        assert torch.equal(l1[0], lat_b[f]), f
+    perm = g.permutation(n_f)
+    lat_p, _, _, _ = opt.shape_opt_deepsdf_batch(lat[perm].clone(), T0.clone(), [pts[i] for i in perm])
+    assert torch.equal(lat_p, lat_b[perm])
+    # objective of the latent-only loop (optimizer.py:306-429): mean squared SDF + code regulariser, before vs after
+    def objective(lv, f):
+        s = dec.sdf(lv, torch.from_numpy(pts[f]).cuda()).double()
+        return float((s * s).mean()) * float(cfg["opt"]["weight"]["w_recon"]) + float(cfg["opt"]["weight"]["w_codereg"]) * float((lv.double() ** 2).sum())
+    worse = sum(objective(lat_b[f], f) > objective(lat[f], f) * (1 + 1e-6) for f in range(0, n_f, 7))
+    assert worse == 0
+    f = 5
+    ref = lat0[f].astype(np.float64).copy()
+    O.shape_opt_deepsdf(oracle_decoder(np.float64), cfg, ref, np.eye(4), pts[f])
+    np.testing.assert_allclose(lat_b[f].cpu().numpy(), ref, rtol=2e-3, atol=2e-5)
