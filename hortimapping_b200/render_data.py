@@ -20,19 +20,35 @@ from ._lib import check
 MAX_IDS = 1024
 
 
+def compact_ids(id_img: np.ndarray):
+    """Map the ids of a frame onto 0 .. n-1 (device table rows).  Returns (int32 image of table rows, {id: row}, exact) where
+    `exact` is False if the image holds non-integral values (they can never equal an integer submap id and get row -1).
+    Ids are arbitrary integers in the reference (`submap_id_img == submap_id`, utils.py:50); the device table has MAX_IDS rows,
+    so ids are compacted per frame instead of being used as indices."""
+    ids = np.ascontiguousarray(id_img)
+    as_int = ids.astype(np.int64, copy=False) if np.issubdtype(ids.dtype, np.integer) else np.rint(ids).astype(np.int64)
+    integral = np.issubdtype(ids.dtype, np.integer) or bool(np.array_equal(as_int, ids))
+    if not integral:
+        mask = as_int == ids
+    uniq, inv = np.unique(as_int, return_inverse=True)
+    rows = inv.reshape(ids.shape).astype(np.int32)
+    if not integral:
+        rows = np.where(mask, rows, -1).astype(np.int32)
+    if uniq.shape[0] > MAX_IDS:
+        raise ValueError(f"a frame with {uniq.shape[0]} distinct ids exceeds the device table ({MAX_IDS} rows)")
+    return rows, {int(v): i for i, v in enumerate(uniq)}, integral
+
+
 class _Frame:
     """Device copies of one frame + the per-id (count, min_v, max_v, min_u, max_u) table."""
 
     def __init__(self, id_img: np.ndarray, depth_img: np.ndarray, dev: torch.device):
         L = _lib.lib()
         self.h, self.w = int(id_img.shape[0]), int(id_img.shape[1])
-        ids = np.ascontiguousarray(id_img).astype(np.int64, copy=False)
-        self.exact = bool(np.array_equal(ids, id_img))                      # non-integral id images cannot match an integer id
-        self.max_id = int(ids.max()) if ids.size else 0
-        self.id_dev = torch.from_numpy(np.where((ids >= 0) & (ids < 2 ** 31 - 1), ids, -1).astype(np.int32)).to(dev)
+        rows, self.row_of, _ = compact_ids(id_img)
+        self.id_dev = torch.from_numpy(rows).to(dev)
         self.depth_dev = torch.from_numpy(np.ascontiguousarray(depth_img, np.float32)).to(dev)
-        self.depth_is_f32 = depth_img.dtype == np.float32
-        n_ids = min(max(self.max_id + 1, 1), MAX_IDS)
+        n_ids = max(len(self.row_of), 1)
         table = torch.empty(n_ids, 5, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             check(L.hm_frame_id_bboxes(None, self.id_dev.data_ptr(), self.depth_dev.data_ptr(), self.h, self.w, n_ids, table.data_ptr(),
@@ -86,9 +102,10 @@ def get_render_data(submap_id, id_imgs, depth_imgs, cam_poses, img_size, invK, c
     sid = int(submap_id) if float(submap_id) == int(submap_id) else None
     for img_id, submap_id_img in id_imgs.items():
         fr = _frame_of(submap_id_img, depth_imgs[img_id], dev)
-        if sid is None or not fr.exact or sid < 0 or sid >= fr.table.shape[0]:
-            continue                                                         # no pixel can match this id (:53-55)
-        count, min_mv, max_mv, min_mu, max_mu = (int(x) for x in fr.table[sid])
+        row = fr.row_of.get(sid) if sid is not None else None
+        if row is None:
+            continue                                                         # no pixel carries this id (:53-55)
+        count, min_mv, max_mv, min_mu, max_mu = (int(x) for x in fr.table[row])
         if count < min_pix_count_match:                                      # :53-55
             continue
         min_v = max(min_mv - bg_pad, 0)                                      # :57-60
@@ -109,7 +126,7 @@ def get_render_data(submap_id, id_imgs, depth_imgs, cam_poses, img_size, invK, c
             pix = torch.empty(2, n, 2, dtype=torch.int32, device=dev)        # [bg | fg] candidates, [u, v]
             dep = torch.empty(2, n, dtype=torch.float32, device=dev)
             counts = torch.empty(2, dtype=torch.int32, device=dev)
-            check(L.hm_crop_candidates(None, fr.id_dev.data_ptr(), fr.depth_dev.data_ptr(), fr.h, fr.w, sid, grid.data_ptr(), crop_h,
+            check(L.hm_crop_candidates(None, fr.id_dev.data_ptr(), fr.depth_dev.data_ptr(), fr.h, fr.w, row, grid.data_ptr(), crop_h,
                                        grid.data_ptr() + 4 * crop_h, crop_w, pix[0].data_ptr(), dep[0].data_ptr(), pix[1].data_ptr(),
                                        dep[1].data_ptr(), counts.data_ptr(), st), "hm_crop_candidates")
             n_bg, n_fg = (int(x) for x in counts.cpu().numpy())

@@ -67,3 +67,22 @@ def test_device_get_render_data_matches_reference_golden(capsys):
     from oracle import render_data_oracle as RO
     pix = np.stack([np.arange(0, 320, 7), np.arange(0, 320, 7) % 240], -1)
     np.testing.assert_array_equal(get_rays(pix, invK), RO.get_rays(pix, invK))
+
+
+def test_compact_ids_host_logic():
+    """Frames carry arbitrary integer ids (utils.py:50 compares with ==); the device table is indexed by compacted rows."""
+    from hortimapping_b200.render_data import compact_ids, MAX_IDS
+    img = np.array([[0, 5, 5], [70000, 5, -3]], np.int32)
+    rows, row_of, exact = compact_ids(img)
+    assert exact and row_of == {-3: 0, 0: 1, 5: 2, 70000: 3} and rows.dtype == np.int32
+    np.testing.assert_array_equal(rows, [[1, 2, 2], [3, 2, 0]])
+    for sid, r in row_of.items():
+        np.testing.assert_array_equal(rows == r, img == sid)
+    rows, row_of, exact = compact_ids(np.array([[0, 1.5], [2.0, 2.0]]))
+    assert not exact and row_of[2] == 1 and rows[0, 1] == -1          # a non-integral pixel matches no integer id
+    g = load_npz("render_data")
+    fid = int(g["frame_ids"][0])
+    rows, row_of, _ = compact_ids(g[f"id_{fid}"])
+    np.testing.assert_array_equal(rows, g[f"id_{fid}"])                # ids 0..5 are already compact
+    with pytest.raises(ValueError):
+        compact_ids(np.arange(MAX_IDS + 1, dtype=np.int32).reshape(1, -1))
