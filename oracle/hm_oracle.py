@@ -39,6 +39,17 @@ def fold_weight_norm(v: np.ndarray, g: np.ndarray) -> np.ndarray:
     return (v * (g / norm)).astype(v.dtype)
 
 
+# Matrix product used by the decoder restatement.  numpy's by default (deterministic across boxes: what the tests pin);
+# bench.py's CPU arm swaps in torch's (the BLAS the reference itself runs on, several times faster than numpy's here).
+_mm = np.matmul
+
+
+def set_matmul(fn=None):
+    """fn(a, b) -> a @ b for 2-D float arrays; None restores numpy's."""
+    global _mm
+    _mm = np.matmul if fn is None else fn
+
+
 @dataclass
 class DecoderOracle:
     """Weights are the folded (weight-norm applied) matrices W_l [out, in] and biases b_l.
@@ -74,7 +85,7 @@ class DecoderOracle:
         for l in range(nl):
             if l in self.latent_in:
                 h = np.concatenate([h, x0], axis=-1)
-            h = h @ self._wt[l] + self.biases[l]
+            h = _mm(h, self._wt[l]) + self.biases[l]
             if l < nl - 1:
                 m = h > 0
                 h = np.where(m, h, 0).astype(self.dtype)
@@ -96,7 +107,7 @@ class DecoderOracle:
         d = (1 - yt * yt).astype(self.dtype)                    # tanh'
         g_skip = np.zeros_like(x0)
         for l in range(nl - 1, -1, -1):
-            d = d @ self.weights[l]                             # back through lin_l
+            d = _mm(d, self.weights[l])                         # back through lin_l
             if l in self.latent_in:
                 nin = x0.shape[1]
                 g_skip = g_skip + d[:, -nin:]
