@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fruits/sec of the shape-completion inner loop on B200 (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): 64 synthetic fruit instances x 2048 observed surface points x
+Headline workload (BASELINE.json configs[1]): 64 synthetic fruit instances x 2048 observed surface points x
 200 LM iterations per GPU, decoder-only path = `Optimizer.shape_opt_deepsdf`
 (wild_completion/optimizer.py:306-429) batched over the fruits, all epsilon_* = 0 so no fruit exits
 early ("200 Adam iters" in BASELINE.json is the reference's LM loop).
@@ -10,10 +10,20 @@ A step = one batched optimise call (64 fruits x 200 iterations).  `value` times 
 resident in HBM; `e2e` times the same K steps through the C-ABI host-buffer entry point
 (hm_optimize_shape_host: pinned host inputs -> H2D -> loop -> D2H of latents/poses/iter counts).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+The same JSON line carries a `joint` record: the FULL path north_star describes (`shape_pose_joint_opt`,
+optimizer.py:28-302: render loss + recon loss + Sim(3) + latent), 32 fruits/GPU x (10 frames x 400 rays x 30
+samples + 2048 points) x 200 LM iterations, with its own value / e2e / roofline (exact device-side row
+counts) / cpu_baseline / parity.
+
+At N = 1 rank 0 also runs the CPU baseline (`cpu_baseline`): the UNMODIFIED reference staged under
+baseline/_ref (scripts/vendor_reference.py) on the host cores when it is there (kind "reference"), else the
+numpy oracle port (kind "port"), in a subprocess, on fruit 0 of the same inputs; its result doubles as the in-run
+parity check of the headline (`parity`: GPU latent after 200 iterations vs the CPU run's).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|reference-cuda]
 N > 1 runs under torchrun (one rank per GPU, fruits sharded, one NCCL all-gather of the 49-float result
-records per step).  `--impl reference` times the CPU oracle port (the reference's algorithm restated in
-numpy, oracle/hm_oracle.py) on the host cores.
+records per step).  `--impl reference` times the reference's own CPU implementation alone (rank 0 only);
+`--impl reference-cuda` the unmodified reference in PyTorch eager on cuda:0.
 """
 from __future__ import annotations
 
@@ -25,12 +35,13 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 if "reference" in sys.argv:
     # the CPU arm uses every host core, also under torchrun (which exports OMP_NUM_THREADS=1 to each rank):
-    # the BLAS thread pools read these variables when numpy is imported
+    # the BLAS thread pools read these variables when numpy / torch are imported
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count())
 
@@ -41,8 +52,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_FRUITS, N_PTS, N_ITERS = 64, 2048, 200
-FLOP_PER_JAC_ROW = 7_342_080           # 2 x 1 835 520 MAC forward + the same backward
+N_JOINT, N_JOINT_DISTINCT = 32, 8          # joint record: fruits per GPU (8 distinct synthetic fruits, each 4 times)
+FLOP_PER_FWD_ROW = 3_671_040           # 2 x 1 835 520 MAC
+FLOP_PER_JAC_ROW = 7_342_080           # forward + the same MAC count backward to the input
 METRIC = "fruits/sec (200 iters, 2048 pts)"
+PARITY_TOL = 1e-4                      # north_star: 1e-4 fp32 relative tolerance
 
 WILD_CFG = {
     "device": "cuda",
@@ -105,128 +119,214 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(dec, codes, seed: int, rank: int):
-    """Synthetic fruits of the SURVEY 8d generator (points only), built with the product decoder."""
+def product_sdf_jac(dec):
     import torch
-    from hortimapping_b200 import synth
 
     def sdf_jac(latent, pts):
         y, g = dec.sdf_jacobian(torch.from_numpy(np.asarray(latent, np.float32)), torch.from_numpy(np.asarray(pts, np.float32)))
         return y.reshape(-1).cpu().numpy(), g.reshape(-1, 35)[:, 32:].cpu().numpy()
+    return sdf_jac
 
+
+def make_inputs(dec, codes, seed: int, rank: int):
+    """Synthetic fruits of the SURVEY 8d generator (points only), built with the product decoder."""
+    from hortimapping_b200 import synth
     pts, T_ow = [], []
     if os.environ.get("HM_BENCH_RANDOM_POINTS"):       # profiling aid: skip the surface projection launches
         g = np.random.default_rng(seed + rank)
         p = ((g.random((N_FRUITS, N_PTS, 3)) * 2 - 1) * 0.045).astype(np.float32)
         return p, np.tile(np.eye(4, dtype=np.float32), (N_FRUITS, 1, 1)), np.tile(codes.mean(0).astype(np.float32), (N_FRUITS, 1))
+    sj = product_sdf_jac(dec)
     for i in range(N_FRUITS):
-        fr = synth.make_fruit(sdf_jac, codes, seed, rank * N_FRUITS + i, n_pts=N_PTS, with_rays=False)
+        fr = synth.make_fruit(sj, codes, seed, rank * N_FRUITS + i, n_pts=N_PTS, with_rays=False)
         pts.append(fr.points_w)
         T_ow.append(np.linalg.inv(fr.T_wo_gt.astype(np.float64)).astype(np.float32))   # pose known for the DeepSDF baseline
     init_lat = np.tile(codes.mean(0).astype(np.float32), (N_FRUITS, 1))
     return np.stack(pts), np.stack(T_ow), init_lat
 
 
-def blas_threads() -> int:
-    """Threads the numpy BLAS pool will actually use (threadpoolctl), raised to the core count when possible."""
-    try:
-        from threadpoolctl import threadpool_info, threadpool_limits
-        threadpool_limits(limits=os.cpu_count(), user_api="blas")
-        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
-        return max(n) if n else 1
-    except Exception:
-        return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+def make_joint_inputs(dec, codes, seed: int, rank: int):
+    """SURVEY 8d generator with rays: 10 frames x (200 fg + 200 bg) rays, 2048 points, 20 % of the background rays carry
+    a depth in front of the fruit (a synthetic leaf) so that the occlusion branch of loss.py:132-149 is exercised."""
+    from hortimapping_b200 import synth
+    sj = product_sdf_jac(dec)
+    return [synth.make_fruit(sj, codes, seed, rank * N_JOINT_DISTINCT + i, n_pts=N_PTS, with_rays=True, leaf_fraction=0.2)
+            for i in range(N_JOINT_DISTINCT)]
 
 
-_BLAS_CHOICE = None
-
-
-def use_fastest_blas(O):
-    """The reference's CPU path is PyTorch; the port's time is > 90 % GEMMs.  Time one decoder-sized GEMM with numpy's BLAS and
-    with torch's (all cores) and run the port on the faster one, so that the CPU arm is not handicapped by the slower library
-    of the box.  Returns (name, threads)."""
-    global _BLAS_CHOICE
-    if _BLAS_CHOICE is not None:
-        return _BLAS_CHOICE
+# ------------------------------------------------------------------------------------------------
+# CPU / reference arms (never on the product path)
+# ------------------------------------------------------------------------------------------------
+def _torch_mm():
     import torch
-    try:
-        torch.set_num_threads(os.cpu_count())
-    except Exception:
-        pass
-    g = np.random.default_rng(0)
-    a, w = g.random((N_PTS, 512), dtype=np.float32), g.random((512, 512), dtype=np.float32)
+    torch.set_num_threads(os.cpu_count())
 
-    def mm_torch(x, y):
+    def mm(x, y):
         return torch.from_numpy(np.ascontiguousarray(x)).matmul(torch.from_numpy(np.ascontiguousarray(y))).numpy()
-
-    def best_of(fn):
-        fn(a, w)
-        ts = []
-        for _ in range(7):
-            t0 = time.perf_counter()
-            fn(a, w)
-            ts.append(time.perf_counter() - t0)
-        return min(ts)
-    t_np, t_th = best_of(np.matmul), best_of(mm_torch)
-    if t_th < t_np:
-        O.set_matmul(mm_torch)
-        _BLAS_CHOICE = (f"torch BLAS ({t_th * 1e3:.1f} ms per 2048x512x512 GEMM vs numpy {t_np * 1e3:.1f} ms)", torch.get_num_threads())
-    else:
-        O.set_matmul(None)
-        _BLAS_CHOICE = (f"numpy BLAS ({t_np * 1e3:.1f} ms per 2048x512x512 GEMM vs torch {t_th * 1e3:.1f} ms)", blas_threads())
-    return _BLAS_CHOICE
+    return mm, torch.get_num_threads()
 
 
-def cpu_baseline_sample(n_iters: int, points_w, T_ow, init_lat):
-    """The oracle port on the host cores: ONE fruit x 2048 points x n_iters LM iterations, scaled to 200."""
+def cpu_arm(io: dict, n_shape_iters: int, n_joint_iters: int, want_states: bool, device: str = "cpu") -> dict:
+    """Runs the reference's own implementation of the path on `io` (fruit 0 of the bench inputs, or synthetic points):
+    the unmodified reference through oracle/ref_runner.py when it is staged, else the numpy oracle port with its GEMMs on
+    torch's CPU BLAS (the library the reference itself runs on).  Returns timings and the resulting states."""
+    from oracle import ref_runner
+    out = {"device": device}
+    cfg = copy.deepcopy(WILD_CFG)
+    if ref_runner.reference_root() is not None:
+        R = ref_runner.ReferenceRunner(device=device)
+        out.update(kind="reference", cores=R.threads,
+                   what=f"unmodified reference ({os.path.relpath(R.root, ROOT) if R.root.startswith(ROOT) else R.root}) via oracle/ref_shim.py, "
+                        f"PyTorch {'CPU, ' + str(R.threads) + ' threads' if device == 'cpu' else 'eager on ' + device}")
+        if n_shape_iters:
+            R.shape_opt(cfg, io["init_lat"], io["T_ow"], io["points_w"], 2)       # warm-up (allocator, BLAS thread pool)
+            lat, it, dt = R.shape_opt(cfg, io["init_lat"], io["T_ow"], io["points_w"], n_shape_iters)
+            out.update(shape_s=dt, shape_iters=it, shape_latent=lat.tolist())
+        if n_joint_iters and "rd" in io:
+            args = (io["j_init_lat"], io["j_init_T"], io["rd"], io["j_points_w"], 0.08, False)
+            if want_states:
+                ob = R.observed_joint_iteration(cfg, *args)
+                out["joint_it0"] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in ob.items()}
+            lat, T, it, dt = R.joint_opt(cfg, *args, n_joint_iters)
+            out.update(joint_s=dt, joint_iters=it)
+        return out
+    if device != "cpu":
+        raise RuntimeError("reference-cuda needs the unmodified reference under baseline/_ref (scripts/vendor_reference.py)")
     from oracle import hm_oracle as O
-    use_fastest_blas(O)
+    mm, threads = _torch_mm()
+    O.set_matmul(mm)
     W, b, _ = load_weights()
     dec = O.DecoderOracle(W, b, (4,), np.float32)
-    cfg = copy.deepcopy(WILD_CFG)
-    cfg["opt"]["converge"]["max_iter"] = n_iters
-    lat = init_lat.copy()
-    t0 = time.perf_counter()
-    O.shape_opt_deepsdf(dec, cfg, lat, T_ow, points_w)
-    dt = time.perf_counter() - t0
-    return 1.0 / (dt * N_ITERS / n_iters), dt
+    out.update(kind="port", cores=threads, what=f"oracle/hm_oracle.py (numpy restatement, GEMMs on torch's CPU BLAS, {threads} threads)")
+    if n_shape_iters:
+        c = copy.deepcopy(cfg)
+        c["opt"]["converge"]["max_iter"] = 2
+        O.shape_opt_deepsdf(dec, c, io["init_lat"].copy(), io["T_ow"], io["points_w"])
+        c["opt"]["converge"]["max_iter"] = n_shape_iters
+        lat = io["init_lat"].copy()
+        t0 = time.perf_counter()
+        _, _, it = O.shape_opt_deepsdf(dec, c, lat, io["T_ow"], io["points_w"])
+        out.update(shape_s=time.perf_counter() - t0, shape_iters=it, shape_latent=lat.tolist())
+    if n_joint_iters and "rd" in io:
+        c = copy.deepcopy(cfg)
+        c["opt"]["converge"]["max_iter"] = n_joint_iters
+        lat = io["j_init_lat"].copy()
+        tr = O.OptTrace()
+        t0 = time.perf_counter()
+        _, _, it = O.shape_pose_joint_opt(dec, c, lat, io["j_init_T"], io["rd"], io["j_points_w"], 0.08, False, trace=tr)
+        out.update(joint_s=time.perf_counter() - t0, joint_iters=it)
+        if want_states:
+            c1 = copy.deepcopy(cfg)
+            c1["opt"]["converge"]["max_iter"] = 1
+            t1 = O.OptTrace()
+            l1 = io["j_init_lat"].copy()
+            _, T1, _ = O.shape_pose_joint_opt(dec, c1, l1, io["j_init_T"], io["rd"], io["j_points_w"], 0.08, False, trace=t1)
+            out["joint_it0"] = {"H": t1.H[0].tolist(), "b": t1.b[0].tolist(), "dx": t1.dx[0].tolist(), "rows_fwd": int(t1.rows_fwd),
+                                "rows_jac": int(t1.rows_grad), "latent": l1.tolist(), "T_ow": np.asarray(T1).tolist()}
+    return out
 
 
-def synth_points_cpu(seed=0):
-    """Inputs for the CPU arm without touching the GPU: random points near the mean shape's surface are not
-    needed for timing -- any 2048 points in the object cube cost the same FLOPs."""
+def save_io(path, io):
+    flat = {k: v for k, v in io.items() if k != "rd"}
+    if "rd" in io:
+        flat["rd_n"] = np.int32(len(io["rd"]["T_wc"]))
+        for k in ("T_wc", "rays_fg", "rays_bg", "depth_fg", "depth_bg"):
+            for i, a in enumerate(io["rd"][k]):
+                flat[f"rd_{k}_{i}"] = np.asarray(a, np.float32)
+    np.savez(path, **flat)
+
+
+def load_io(path):
+    with np.load(path) as z:
+        io = {k: z[k] for k in z.files if not k.startswith("rd_")}
+        if "rd_n" in z.files:
+            n = int(z["rd_n"])
+            io["rd"] = {k: [z[f"rd_{k}_{i}"] for i in range(n)] for k in ("T_wc", "rays_fg", "rays_bg", "depth_fg", "depth_bg")}
+    return io
+
+
+def synth_io_cpu(seed=0):
+    """Inputs for the stand-alone reference arm without touching the GPU: any 2048 points in the object cube cost the
+    same FLOPs (the decoder-only loop's work does not depend on the data)."""
     g = np.random.default_rng(seed)
-    pts = ((g.random((N_PTS, 3)) * 2 - 1) * 0.045).astype(np.float32)
-    return pts, np.eye(4, dtype=np.float32)
+    _, _, codes = load_weights()
+    return {"points_w": ((g.random((N_PTS, 3)) * 2 - 1) * 0.045).astype(np.float32), "T_ow": np.eye(4, dtype=np.float32),
+            "init_lat": codes.mean(0).astype(np.float32)}
 
 
 def run_reference(args):
+    """`--impl reference` / `--impl reference-cuda`: the reference's own implementation alone, same metric and config.
+    A step is a bounded sample of the workload: ONE fruit x HM_BENCH_REF_ITERS (default 100) of the 200 iterations."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    W, b, codes = load_weights()
-    pts, T = synth_points_cpu()
-    init = codes.mean(0).astype(np.float32)
-    n_it = int(os.environ.get("HM_BENCH_REF_ITERS", "100"))      # iterations per step (the test suite uses a short sample)
-    from oracle import hm_oracle as O
-    blas_name, threads = use_fastest_blas(O)
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline_sample(4, pts, T, init)
-    times = []
-    for _ in range(args.steps):
-        v, dt = cpu_baseline_sample(n_it, pts, T, init)
-        times.append(dt)
-    step_s = sum(times) / len(times)
+    device = "cuda" if args.impl == "reference-cuda" else "cpu"
+    n_it = int(os.environ.get("HM_BENCH_REF_ITERS", "100"))
+    io = load_io(args.io) if args.io else synth_io_cpu()
+    if args.io:                                    # child of the b200 arm: one full unit + the joint sample, states returned
+        res = cpu_arm(io, N_ITERS, int(os.environ.get("HM_BENCH_REF_JOINT_ITERS", "10")), True, device)
+        print("HM_CPU_ARM " + json.dumps(res))
+        return
+    try:
+        for _ in range(min(args.warmup, 1)):
+            cpu_arm(io, 4, 0, False, device)
+        times, info = [], None
+        for _ in range(args.steps):
+            info = cpu_arm(io, n_it, 0, False, device)
+            times.append(info["shape_s"])
+    except Exception as e:                          # e.g. reference-cuda without a GPU or without baseline/_ref
+        print(json.dumps({"impl": args.impl, "unavailable": f"{type(e).__name__}: {e}"[:300]}))
+        return
+    step_s = statistics.median(times)
     value = 1.0 / (step_s * N_ITERS / n_it)
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "fruits/s", "n_gpus": args.gpus, "steps": args.steps,
+    sample = f"{info['what']}: shape_opt_deepsdf, 1 fruit x {N_PTS} pts x {n_it} of {N_ITERS} iterations per step (median of {len(times)} steps), scaled x{N_ITERS / n_it:g}"
+    out = {"impl": args.impl, "metric": METRIC, "value": value, "unit": "fruits/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": "64 fruits x 2048 pts x 200 LM iters, decoder-only (shape_opt_deepsdf)",
-                      "sample": f"1 fruit x {N_PTS} pts x {n_it} of 200 iterations per step, scaled x{N_ITERS / n_it:g}"},
-           "cpu_baseline": {"value": value, "unit": "fruits/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                            "sample": f"oracle/hm_oracle.py shape_opt_deepsdf on {blas_name}, 1 fruit x {N_PTS} pts x {n_it} iterations, scaled to 200"},
+                      "sample": f"1 fruit x {N_PTS} pts x {n_it} of 200 iterations per step, scaled x{N_ITERS / n_it:g}",
+                      "step_spread": {"min_s": min(times), "max_s": max(times)}},
+           "cpu_baseline": {"value": value, "unit": "fruits/s", "cores": info["cores"], "host_cores": os.cpu_count(), "kind": info["kind"],
+                            "sample": sample},
            "e2e": {"value": value, "unit": "fruits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
+
+
+def run_cpu_child(io: dict) -> dict | None:
+    """The CPU baseline leg of the b200 arm: a child process (own BLAS thread settings, `.cuda()` neutralised there only)."""
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "io.npz")
+        save_io(path, io)
+        env = dict(os.environ)
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            env[v] = str(os.cpu_count())
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        for v in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(v, None)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--io", path], env=env,
+                           capture_output=True, text=True, timeout=900)
+        for line in r.stdout.splitlines():
+            if line.startswith("HM_CPU_ARM "):
+                return json.loads(line[len("HM_CPU_ARM "):])
+        sys.stderr.write("cpu baseline child failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return None
+
+
+def peak_tflops():
+    peak, src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    try:
+        pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for key in ("bf16_tflops_sustained", "bf16_tflops"):       # the kernel is timed inside a long, power-capped step
+            if key in pj and float(pj[key]) > 0:
+                return float(pj[key]), f"MEASURED_PEAKS.json {key}"
+    except Exception:
+        pass
+    return peak, src
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
 def main():
@@ -234,10 +334,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--iters", type=int, default=N_ITERS, help=argparse.SUPPRESS)
+    ap.add_argument("--io", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--no-joint", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl != "b200":
         return run_reference(args)
 
     import torch
@@ -245,7 +348,7 @@ def main():
     import __graft_entry__ as ge
     from hortimapping_b200 import _lib
     from hortimapping_b200.decoder import Decoder
-    from hortimapping_b200.optimizer import Optimizer, opt_params_from_cfg
+    from hortimapping_b200.optimizer import Optimizer, PackedBatch, opt_params_from_cfg
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -267,17 +370,68 @@ def main():
     cfg["opt"]["converge"]["max_iter"] = args.iters
     opt = Optimizer(cfg, dec, None, None)
     pts, T_ow, init_lat = make_inputs(dec, codes, seed=7, rank=rank)
+    peak, peak_src = peak_tflops()
 
-    # ---- device-resident arm
-    d_pts = [torch.from_numpy(pts[i]).to(dev) for i in range(N_FRUITS)]
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    params = opt_params_from_cfg(cfg["opt"])
+
+    def timed(step_fn, steps, warmup):
+        """W warm-up steps, then K steps between barrier + synchronize, CUDA events, MAX over ranks; decoder launches are
+        event-timed inside the region (hm_profile_enable) for the roofline."""
+        for _ in range(warmup):
+            step_fn()
+        sync()
+        c0 = dec.counters()
+        dec.profile(True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        ev0.record()
+        res = None
+        for _ in range(steps):
+            res = step_fn()
+        ev1.record()
+        sync()
+        clocks = sampler.stop()
+        dec.profile(False)
+        c1 = dec.counters()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), {k: c1[k] - c0[k] for k in c1}, clocks, res
+
+    def roofline_of(dc, total_ms, kernel):
+        flop = dc["rows_forward"] * FLOP_PER_FWD_ROW + dc["rows_jacobian"] * FLOP_PER_JAC_ROW
+        n_launch, dec_ms = dc["decoder_launches"], dc["decoder_ms"]
+        achieved = flop / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else None
+        tiles = dc["tiles_forward"] + dc["tiles_jacobian"]
+        dead = dc["tiles_dead_forward"] + dc["tiles_dead_jacobian"]
+        r = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+             "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+             "rows_forward": dc["rows_forward"], "rows_jacobian": dc["rows_jacobian"], "rows_counted": "exact (device-side counters)",
+             "algorithmic_flop_per_launch": flop / max(n_launch, 1), "launches": n_launch, "avg_launch_ms": dec_ms / max(n_launch, 1),
+             "forward_launches": dc["forward_launches"], "forward_ms": dc["forward_ms"],
+             "jacobian_launches": dc["jacobian_launches"], "jacobian_ms": dc["jacobian_ms"],
+             "tiles": tiles, "tiles_zero_operand_shortcut": dead,
+             "kernel_share_of_step": dec_ms / total_ms if total_ms > 0 else None}
+        tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tfile):       # one ncu --set full capture of this kernel (static file, named so it can go stale visibly)
+            tj = json.load(open(tfile))
+            r["traffic"] = tj.get("dram_bytes_per_launch")
+            r["ncu_capture"] = {k: tj.get(k) for k in ("tensor_pipe_active_pct", "source", "kernel", "rows_per_launch")}
+        return r
+
+    # ================================================================== headline: decoder-only loop, device-resident
     lat0 = torch.from_numpy(init_lat).to(dev)
     T0 = torch.from_numpy(T_ow).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     gathered = torch.empty(world * N_FRUITS, 49, device=dev)
-
-    from hortimapping_b200.optimizer import PackedBatch
     pk = PackedBatch([p for p in pts], None, 0, np.zeros(N_FRUITS, np.float32), np.zeros(N_FRUITS, bool))
-    params = opt_params_from_cfg(cfg["opt"])
 
     def step_device():
         lat, T = lat0.clone(), T0.clone()
@@ -288,63 +442,13 @@ def main():
         else:
             gathered.copy_(rec)
         flush.zero_()
-        return lat, iters
+        return lat, iters, status
 
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    sync()
-    c0 = dec.counters()
-    dec.profile(True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    ev0.record()
-    for _ in range(args.steps):
-        lat_out, iters_out = step_device()
-    ev1.record()
-    sync()
-    clocks = sampler.stop()
-    dec.profile(False)
-    c1 = dec.counters()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    total_ms, dc, clocks, (lat_out, iters_out, status_out) = timed(step_device, args.steps, args.warmup)
     assert int(iters_out.min().item()) == args.iters, "a fruit exited early: the workload is not fixed"
     value = world * N_FRUITS * args.steps / (total_ms / 1e3) * (args.iters / N_ITERS)   # --iters != 200 is a debug aid only
-
-    # ---- roofline of the dominant kernel (tc_decoder_kernel<jac>), timed live with CUDA events inside the step
-    n_launch = c1["decoder_launches"] - c0["decoder_launches"]
-    dec_ms = c1["decoder_ms"] - c0["decoder_ms"]
-    rows_per_launch = N_FRUITS * N_PTS
-    flop_per_launch = rows_per_launch * FLOP_PER_JAC_ROW
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
-    try:
-        pk_json = json.load(open(peaks_file))
-        for key in ("bf16_tflops_sustained", "bf16_tflops"):       # the kernel is timed inside a long, power-capped step
-            if key in pk_json and float(pk_json[key]) > 0:
-                peak, peak_src = float(pk_json[key]), f"MEASURED_PEAKS.json {key} (of measured)"
-                break
-    except Exception:
-        pass
-    achieved = flop_per_launch / (dec_ms / max(n_launch, 1) * 1e-3) / 1e12 if n_launch else None
-    traffic, tensor_pct = None, None
-    tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tfile):
-        tj = json.load(open(tfile))
-        traffic, tensor_pct = tj.get("dram_bytes_per_launch"), tj.get("tensor_pipe_active_pct")
-    roofline = {"bound": "tensor", "kernel": "tc_decoder_kernel<true> (fused DeepSDF forward + input gradient)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "tensor_pipe_active_pct_ncu": tensor_pct, "peak_source": peak_src, "algorithmic_flop_per_launch": flop_per_launch,
-                "issued_mma_flop_per_launch": 3 * flop_per_launch, "launches": n_launch, "avg_launch_ms": dec_ms / max(n_launch, 1),
-                "kernel_share_of_step": dec_ms / total_ms}
+    roofline = roofline_of(dc, total_ms, "tc_decoder_kernel<true> (fused DeepSDF forward + input gradient)")
+    launches = dc["kernel_launches"]
 
     # ---- end-to-end arm: C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
     h_lat = torch.from_numpy(init_lat).pin_memory()
@@ -378,7 +482,6 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * N_FRUITS * args.steps / float(e2e_s.item()) * (args.iters / N_ITERS)
     assert torch.allclose(w_lat.to(dev), lat_out, rtol=0, atol=0), "host and device arms disagree"
-    launches = c1["kernel_launches"] - c0["kernel_launches"]
 
     out = {"metric": METRIC, "value": value, "unit": "fruits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -388,21 +491,141 @@ def main():
                       "parallelism": f"fruits sharded over {world} GPU(s), one all-gather of 49-float records per step",
                       "l2": "256 MiB buffer written between steps (L2 flush); weights are L2-resident by design within a step",
                       "arithmetic": "fp32 semantics: operands split into fp16 hi+lo, three products (A_hi x W_lo, A_lo x W_hi, A_hi x W_hi) as M=128 "
-                                    "cta_group::2 tcgen05 MMAs into one fp32 TMEM accumulator per 2 k-chunks, partials summed in fp32 RN registers"},
+                                    "cta_group::2 tcgen05 MMAs into one fp32 TMEM accumulator per 2 k-chunks, partials summed in fp32 RN registers; "
+                                    "MMAs whose A operand is exactly zero for a whole tile pair (dead lin3 of the shipped models) are not issued"},
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": "fruits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-           "roofline": roofline}
+           "roofline": roofline, "f16_saturated_fruits": int((status_out & 0x40).ne(0).sum().item())}
+
+    # ================================================================== joint record: the full shape + pose loop
+    joint_io = {}
+    if not args.no_joint:
+        fruits = make_joint_inputs(dec, codes, seed=7, rank=rank)
+        rds = [fruits[i % N_JOINT_DISTINCT].render_data for i in range(N_JOINT)]
+        jpts = [fruits[i % N_JOINT_DISTINCT].points_w for i in range(N_JOINT)]
+        jlat0 = torch.from_numpy(np.tile(codes.mean(0).astype(np.float32), (N_JOINT, 1))).to(dev)
+        jT0 = torch.eye(4, device=dev).repeat(N_JOINT, 1, 1).contiguous()
+        jpk = PackedBatch(jpts, rds, cfg["opt"]["render"]["n_frame"], np.full(N_JOINT, 0.08, np.float32), np.zeros(N_JOINT, bool))
+        jgathered = torch.empty(world * N_JOINT, 49, device=dev)
+
+        def jstep_device():
+            lat, T = jlat0.clone(), jT0.clone()
+            iters, status = opt._run(jpk, lat, T, params)
+            rec = torch.cat([lat, T.reshape(N_JOINT, 16), iters.float().reshape(-1, 1)], 1)
+            if world > 1:
+                dist.all_gather_into_tensor(jgathered, rec)
+            else:
+                jgathered.copy_(rec)
+            flush.zero_()
+            return lat, T, iters, status
+
+        j_steps = max(1, min(args.steps, 2))
+        j_ms, jdc, jclocks, (jlat, jT, jit, jst) = timed(jstep_device, j_steps, 1)
+        assert int(jit.min().item()) == args.iters, "joint: a fruit exited early: the workload is not fixed"
+        j_value = world * N_JOINT * j_steps / (j_ms / 1e3) * (args.iters / N_ITERS)
+        # e2e through hm_optimize_joint_host (host buffers in, results out)
+        hp = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hj = {"lat": hp(np.tile(codes.mean(0).astype(np.float32), (N_JOINT, 1))), "T": hp(np.tile(np.eye(4, dtype=np.float32), (N_JOINT, 1, 1))),
+              "pts": hp(jpk.points), "Twc": hp(jpk.T_wc), "rays": hp(jpk.rays), "dobs": hp(jpk.depth_obs),
+              "it": torch.zeros(N_JOINT, dtype=torch.int32).pin_memory(), "st": torch.zeros(N_JOINT, dtype=torch.int32).pin_memory()}
+        jb = _lib.FruitBatch()
+        jb.n_fruits = N_JOINT
+        jb.d_points_w, jb.h_point_offsets = hj["pts"].data_ptr(), jpk.point_offsets.ctypes.data
+        jb.h_frame_offsets, jb.d_T_wc = jpk.frame_offsets.ctypes.data, hj["Twc"].data_ptr()
+        jb.h_ray_offsets, jb.h_n_fg = jpk.ray_offsets.ctypes.data, jpk.n_fg.ctypes.data
+        jb.d_rays, jb.d_depth_obs = hj["rays"].data_ptr(), hj["dobs"].data_ptr()
+        jb.h_cube_radius, jb.h_pose_known = jpk.cube_radius.ctypes.data, jpk.pose_known.ctypes.data
+        jb.d_iter_count, jb.d_status = hj["it"].data_ptr(), hj["st"].data_ptr()
+        j_h2d = sum(hj[k].numel() * 4 for k in ("lat", "T", "pts", "Twc", "rays", "dobs"))
+        j_d2h = sum(hj[k].numel() * 4 for k in ("lat", "T", "it", "st"))
+
+        def jstep_host():
+            w_lat, w_T = hj["lat"].clone().pin_memory(), hj["T"].clone().pin_memory()
+            jb.d_latents, jb.d_T_ow = w_lat.data_ptr(), w_T.data_ptr()
+            _lib.check(dec._L.hm_optimize_joint_host(dec.handle, C.byref(params), C.byref(jb)), "hm_optimize_joint_host")
+            return w_lat
+
+        sync()
+        t0 = time.perf_counter()
+        wj = jstep_host()
+        torch.cuda.synchronize()
+        je2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(je2e_s, op=dist.ReduceOp.MAX)
+        j_e2e = world * N_JOINT / float(je2e_s.item()) * (args.iters / N_ITERS)
+        n_it_total = args.iters * j_steps
+        out["joint"] = {
+            "metric": "fruits/sec (200 iters, 2048 pts + 10 frames x 400 rays x 30 samples), shape_pose_joint_opt",
+            "value": j_value, "unit": "fruits/s", "steps": j_steps, "warmup": 1, "ms_per_step": j_ms / j_steps,
+            "config": {"workload": f"{N_JOINT} fruits/GPU ({N_JOINT_DISTINCT} distinct synthetic fruits x {N_JOINT // N_JOINT_DISTINCT}) x (10 frames x (200 fg + 200 bg) rays x 30 samples "
+                                   f"+ {N_PTS} pts) x {args.iters} LM iters, Sim(3) + latent (optimizer.py:28-302), configs/wild_pepper.yaml, epsilons 0, "
+                                   "20 % leaf-occluded background rays"},
+            "e2e": {"value": j_e2e, "unit": "fruits/s", "h2d_bytes_per_step": j_h2d, "d2h_bytes_per_step": j_d2h, "steps": 1},
+            "host_equals_device": bool(torch.equal(wj.to(dev), jlat)),
+            "roofline": roofline_of(jdc, j_ms, "tc_decoder_kernel<false> (in-sphere ray samples, forward) + tc_decoder_kernel<true> (recon points + in-band samples)"),
+            "rows_per_fruit_iteration": {"forward": jdc["rows_forward"] / (N_JOINT * n_it_total), "forward_plus_gradient": jdc["rows_jacobian"] / (N_JOINT * n_it_total)},
+            "clocks": jclocks, "gpu_launches": jdc["kernel_launches"], "status_bits_seen": sorted({hex(int(x)) for x in jst.cpu().tolist()})}
+        f0 = fruits[0]
+        joint_io = {"j_init_lat": f0.init_latent, "j_init_T": f0.init_T_ow, "j_points_w": f0.points_w, "rd": f0.render_data}
+        # iteration 0 of fruit 0 on the device for the in-run parity check (single-fruit call): the LM system, the exact row counts
+        # and the state after the step
+        c_a = dec.counters()
+        l1 = torch.from_numpy(f0.init_latent.copy()).to(dev).reshape(1, 32)
+        T1 = torch.from_numpy(f0.init_T_ow.copy()).to(dev).reshape(1, 4, 4)
+        opt.shape_pose_joint_opt_batch(l1, T1, [f0.render_data], [f0.points_w], 0.08, False, max_iter=1)
+        gH, gb, gdx = (t.cpu().numpy()[0] for t in opt.last_system(1))
+        c_b = dec.counters()
+        g_it0 = {"H": gH, "b": gb, "dx": gdx, "latent": l1[0].cpu().numpy(), "T_ow": T1[0].cpu().numpy(),
+                 "rows_fwd": c_b["rows_forward"] - c_a["rows_forward"], "rows_jac": c_b["rows_jacobian"] - c_a["rows_jacobian"]}
+
+    # ================================================================== CPU baseline + in-run parity (rank 0, N = 1)
+    parity_fail = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        io = {"points_w": pts[0], "T_ow": T_ow[0], "init_lat": init_lat[0]}
+        io.update(joint_io)
+        res = run_cpu_child(io)
+        if res is not None:
+            cv = 1.0 / res["shape_s"]
+            out["cpu_baseline"] = {"value": cv, "unit": "fruits/s", "cores": res["cores"], "host_cores": os.cpu_count(), "kind": res["kind"],
+                                   "sample": f"{res['what']}: shape_opt_deepsdf on fruit 0 of this run, {N_PTS} pts x {res['shape_iters']} iterations "
+                                             f"({res['shape_s']:.1f} s) = one whole unit of the workload"}
+            if args.iters == N_ITERS:
+                e = rel_err(lat_out[0].cpu().numpy(), res["shape_latent"])
+                out["parity"] = {"what": "latent of fruit 0 after 200 LM iterations, B200 vs the CPU baseline run above", "max_rel": e, "tol": PARITY_TOL,
+                                 "ok": bool(e <= PARITY_TOL)}
+                if e > PARITY_TOL:
+                    parity_fail = f"headline parity {e:.3e} > {PARITY_TOL}"
+            if "joint" in out and "joint_s" in res:
+                jv = 1.0 / (res["joint_s"] * N_ITERS / res["joint_iters"])
+                out["joint"]["cpu_baseline"] = {"value": jv, "unit": "fruits/s", "cores": res["cores"], "host_cores": os.cpu_count(), "kind": res["kind"],
+                                                "sample": f"{res['what']}: shape_pose_joint_opt on fruit 0 of this run, {res['joint_iters']} of {N_ITERS} iterations "
+                                                          f"({res['joint_s']:.1f} s), scaled x{N_ITERS / res['joint_iters']:g} (extrapolated)"}
+                if "joint_it0" in res:
+                    r0 = res["joint_it0"]
+                    # Sample membership is decided by hard thresholds (in-sphere, |sdf| < th, de_do > 1e-6, occlusion): when the device
+                    # and the CPU run select the same NUMBER of rows no sample flipped and H, b must agree to 1e-4; a flipped
+                    # sample changes H, b by up to its own weight (measured <= 5e-3, tests/test_gpu_optimizer.py), which is then allowed.
+                    flips = abs(int(r0["rows_fwd"]) - int(g_it0["rows_fwd"])) + abs(int(r0["rows_jac"]) - int(g_it0["rows_jac"]))
+                    tol_sys = PARITY_TOL if flips == 0 else 5e-3
+                    errs = {k: rel_err(g_it0[k], r0[k]) for k in ("H", "b", "dx", "latent", "T_ow")}
+                    ok = errs["H"] <= tol_sys and errs["b"] <= tol_sys
+                    out["joint"]["parity"] = {"what": "iteration 0 of fruit 0 from the same start, B200 vs the CPU baseline: normal equations H, b (max-norm relative), "
+                                                      "solve dx, state after the step; rows = decoder rows selected by the hard thresholds. dx / state go through "
+                                                      "a 39x39 solve with cond ~1e5 (reference: fp32 torch.inverse, here: fp64 elimination) and are reported, not gated; "
+                                                      "later iterations are compared in tests/ by step replay from the reference's own states (SURVEY.md 7.4)",
+                                              "rows_forward": {"b200": int(g_it0["rows_fwd"]), "cpu": int(r0["rows_fwd"])},
+                                              "rows_forward_plus_gradient": {"b200": int(g_it0["rows_jac"]), "cpu": int(r0["rows_jac"])},
+                                              "membership_flips": flips, **{"rel_" + k: v for k, v in errs.items()}, "max_rel": max(errs["H"], errs["b"]),
+                                              "tol": tol_sys, "ok": bool(ok)}
+                    if not ok:
+                        parity_fail = f"joint parity H {errs['H']:.3e} b {errs['b']:.3e} > {tol_sys}"
     if rank == 0:
-        if world == 1:
-            cv, cdt = cpu_baseline_sample(N_ITERS, pts[0], T_ow[0], init_lat[0])
-            from oracle import hm_oracle as O_
-            blas_name, threads = use_fastest_blas(O_)
-            out["cpu_baseline"] = {"value": cv, "unit": "fruits/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"oracle/hm_oracle.py shape_opt_deepsdf on {blas_name}, 1 fruit x {N_PTS} pts x {N_ITERS} iterations "
-                                             f"({cdt:.1f} s) = one whole unit of the workload"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if parity_fail:
+        sys.stderr.write("bench.py: PARITY FAILURE: " + parity_fail + "\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

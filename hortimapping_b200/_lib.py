@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libhortimapping_b200.so")
 HM_LATENT, HM_IN, HM_HIDDEN, HM_LAYERS = 32, 35, 512, 9
 HM_ENGINE_TC, HM_ENGINE_SIMT = 0, 1
 STATUS = dict(CONV_GRADIENT=0x01, CONV_CODE=0x02, CONV_POSE=0x04, MAX_ITER=0x08, FRAME_SKIPPED=0x10,
-              SUBMAP_INVALID=0x20, F16_SATURATED=0x40)
+              SUBMAP_INVALID=0x20, F16_SATURATED=0x40, SOLVE_FAILED=0x80)
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -46,13 +46,16 @@ class FruitBatch(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("rows_forward", C.c_int64), ("rows_jacobian", C.c_int64), ("kernel_launches", C.c_int64),
-                ("iterations", C.c_int64), ("decoder_launches", C.c_int64), ("decoder_ms", C.c_double)]
+                ("iterations", C.c_int64), ("decoder_launches", C.c_int64), ("decoder_ms", C.c_double),
+                ("forward_launches", C.c_int64), ("forward_ms", C.c_double), ("jacobian_launches", C.c_int64),
+                ("jacobian_ms", C.c_double), ("tiles_forward", C.c_int64), ("tiles_jacobian", C.c_int64),
+                ("tiles_dead_forward", C.c_int64), ("tiles_dead_jacobian", C.c_int64)]
 
 
 _lib = None
 
 # every symbol include/hortimapping_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_calibrate",
+EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_zero_shortcut", "hm_calibrate",
            "hm_get_counters", "hm_saturation_count", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
            "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays"]
@@ -66,7 +69,12 @@ def lib() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(hortimapping_b200 has no CPU/PyTorch fallback)")
-    L = C.CDLL(LIB_PATH)
+    _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(L: C.CDLL) -> C.CDLL:
+    """Declares the argument types of every entry point of include/hortimapping_b200.h on a loaded library."""
     L.hm_last_error.restype = C.c_char_p
     L.hm_version.restype = C.c_int
     L.hm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(DecoderDesc)]
@@ -74,6 +82,7 @@ def lib() -> C.CDLL:
     L.hm_destroy.restype = None
     L.hm_set_engine.argtypes = [C.c_void_p, C.c_int]
     L.hm_get_engine.argtypes = [C.c_void_p]
+    L.hm_set_zero_shortcut.argtypes = [C.c_void_p, C.c_int]
     L.hm_calibrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hm_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.hm_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -103,7 +112,6 @@ def lib() -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.hm_nn_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.hm_isosurface_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
-    _lib = L
     return L
 
 

@@ -16,7 +16,7 @@ void hm_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* hm_last_error(void) { return g_err; }
-extern "C" int hm_version(void) { return 100; }
+extern "C" int hm_version(void) { return 200; }
 
 int hm_ws_reserve(hm_context* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return HM_OK;
@@ -126,7 +126,9 @@ extern "C" void hm_destroy(hm_context* ctx) {
   hm_tc_free(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
-  if (ctx->pinned) cudaFree(ctx->pinned);
+  if (ctx->io_arena) cudaFree(ctx->io_arena);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
   if (ctx->mesh_ws) cudaFree(ctx->mesh_ws);
   if (ctx->mesh_out) cudaFree(ctx->mesh_out);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
@@ -146,19 +148,40 @@ extern "C" int hm_set_engine(hm_context* ctx, int engine) {
 
 extern "C" int hm_get_engine(const hm_context* ctx) { return ctx ? ctx->engine : HM_ERR_INVALID; }
 
+extern "C" int hm_set_zero_shortcut(hm_context* ctx, int on) {
+  HM_CHECK(ctx, "hm_set_zero_shortcut: null context");
+  ctx->zero_shortcut = on ? 1 : 0;
+  return HM_OK;
+}
+
 extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
   HM_CHECK(ctx && out, "hm_get_counters: null argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  HM_CUDA(cudaDeviceSynchronize());
   for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
     float ms = 0.f;
     HM_CUDA(cudaEventSynchronize(ctx->prof_events[i + 1]));
     HM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
     ctx->counters.decoder_ms += ms;
     ctx->counters.decoder_launches += 1;
+    if (ctx->prof_kinds[i / 2]) { ctx->counters.jacobian_ms += ms; ctx->counters.jacobian_launches += 1; }
+    else { ctx->counters.forward_ms += ms; ctx->counters.forward_launches += 1; }
     ctx->prof_pool.push_back(ctx->prof_events[i]);
     ctx->prof_pool.push_back(ctx->prof_events[i + 1]);
   }
   ctx->prof_events.clear();
+  ctx->prof_kinds.clear();
   *out = ctx->counters;
+  if (ctx->d_tc_flags) {      // exact device-side totals of the tensor-core engine (HM_TC_FLAG_* slots, common.cuh)
+    unsigned long long dev[6] = {};
+    HM_CUDA(cudaMemcpy(dev, ctx->d_tc_flags + HM_TC_FLAG_ROWS_FWD, sizeof(dev), cudaMemcpyDeviceToHost));
+    out->rows_forward += (int64_t)dev[0];
+    out->rows_jacobian += (int64_t)dev[1];
+    out->tiles_forward = (int64_t)dev[2];
+    out->tiles_jacobian = (int64_t)dev[3];
+    out->tiles_dead_forward = (int64_t)dev[4];
+    out->tiles_dead_jacobian = (int64_t)dev[5];
+  }
   return HM_OK;
 }
 
@@ -198,7 +221,6 @@ extern "C" int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, voi
 
 int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st) {
   if (rows.n <= 0) return HM_OK;
-  if (d_jac) ctx->counters.rows_jacobian += rows.n; else ctx->counters.rows_forward += rows.n;
   if (ctx->engine == HM_ENGINE_SIMT) return hm_simt_decode(ctx, rows, d_sdf, d_jac, st, nullptr);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profiling) {
@@ -215,6 +237,7 @@ int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, 
     HM_CUDA(cudaEventRecord(e1, st));
     ctx->prof_events.push_back(e0);
     ctx->prof_events.push_back(e1);
+    ctx->prof_kinds.push_back(d_jac ? 1 : 0);
   }
   return rc;
 }

@@ -53,6 +53,17 @@ struct hm_tc_op {
   int64_t blob_offset;           // byte offset of this op's first stage in the weight blob
 };
 
+// int32 slots of hm_context::d_tc_flags (device counters of the tensor-core engine; 64-bit totals take two slots)
+#define HM_TC_FLAG_SAT 0            // thread blocks in which an fp16 operand conversion saturated
+#define HM_TC_FLAG_ROWS_FWD 2       // rows evaluated by forward-only launches
+#define HM_TC_FLAG_ROWS_JAC 4       // rows evaluated by forward + input-gradient launches
+#define HM_TC_FLAG_TILES_FWD 6      // 64-row tiles processed (forward-only / forward + gradient)
+#define HM_TC_FLAG_TILES_JAC 8
+#define HM_TC_FLAG_DEAD_FWD 10      // ... of which took the zero-operand shortcut
+#define HM_TC_FLAG_DEAD_JAC 12
+#define HM_TC_FLAG_DEBUG 32         // wait-cycle counters of the instrumented debug build (HM_TC_COUNTERS)
+#define HM_TC_FLAG_COUNT 128
+
 struct hm_tc_plan {
   hm_tc_op ops[HM_TC_NOPS_ALL];
 };
@@ -78,7 +89,8 @@ struct hm_context {
   float* d_w8 = nullptr;           // [512] lin8 weight, d_b8 scalar in d_b[8]
   uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
   int32_t* d_tc_flags = nullptr;   // saturation counter etc.
-  uint32_t* d_tc_trace = nullptr;  // debug timeline (hm_debug_tc_trace)
+  uint32_t* d_tc_trace = nullptr;  // timeline buffer of the instrumented testing build (NULL in the product)
+  int zero_shortcut = 1;           // tensor-core engine: skip MMAs with an exactly-zero A operand (dead lin3), hm_set_zero_shortcut
   // grow-only workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -89,11 +101,15 @@ struct hm_context {
   void* mesh_out = nullptr;
   size_t mesh_out_bytes = 0;
   int64_t mesh_n_verts = 0, mesh_n_faces = 0;
-  void* pinned = nullptr;
-  size_t pinned_bytes = 0;
+  void* io_arena = nullptr;        // device-side copies of the host buffers of the *_host entry points
+  size_t io_arena_bytes = 0;
+  void* h_stage = nullptr;         // pinned staging of the optimiser's per-call host tables (optimizer.cu stage_reserve)
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_event = nullptr;
   hm_counters counters = {};
   int profiling = 0;
   std::vector<cudaEvent_t> prof_events;      // (begin, end) pairs awaiting read-back
+  std::vector<int> prof_kinds;               // per pair: 0 = forward-only launch, 1 = forward + input gradient
   std::vector<cudaEvent_t> prof_pool;
   // last LM system (test hook)
   float* d_last_H = nullptr;
@@ -116,6 +132,8 @@ struct hm_rows {
   const int32_t* d_row_latent;  // [n] or NULL
   int64_t n;
   const int32_t* d_n_dynamic;   // optional device-side row count (<= n); NULL = use n
+  const int32_t* d_out_index = nullptr;   // optional: the SDF of row i goes to d_sdf[d_out_index[i]] (rows compacted from a larger set)
+  int32_t* d_latent_sat = nullptr;        // optional [L]: the tensor-core engine sets entry l when a row of latent-table row l saturated fp16
   // fused mesher grid (wild_completion/utils.py:542-562): when grid_n > 0 the xyz of row i is create_voxel_grid(grid_n)[i] *
   // grid_radius, generated inside the decoder kernel (d_xyz is ignored; all rows use latent 0)
   int32_t grid_n = 0;

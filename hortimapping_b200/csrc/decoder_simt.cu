@@ -100,8 +100,10 @@ __global__ void build_rows(const float* __restrict__ xyz, const float* __restric
 }
 
 // sdf = tanh(h7 . w8 + b8) (deep_sdf_decoder.py:107-108); optionally d7 = (1 - sdf^2) * w8 * (h7 > 0)
+// out_index (optional): the SDF of row r goes to sdf[out_index[r]].  unit_seed: d7 without the (1 - sdf^2) factor -- the operand the
+// tensor-core engine feeds to its backward GEMMs (it applies the factor to the finished gradient), used when calibrating its scales.
 __global__ void head_kernel(const float* __restrict__ h7, const float* __restrict__ w8, const float* __restrict__ b8,
-                            int64_t n, float* __restrict__ sdf, float* __restrict__ d7) {
+                            int64_t n, float* __restrict__ sdf, const int32_t* __restrict__ out_index, float* __restrict__ d7, int unit_seed) {
   int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= n) return;
@@ -110,9 +112,9 @@ __global__ void head_kernel(const float* __restrict__ h7, const float* __restric
   for (int c = lane; c < HM_HIDDEN; c += 32) s = fmaf(h[c], w8[c], s);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float f = tanhf(s + b8[0]);
-  if (lane == 0) sdf[row] = f;
+  if (lane == 0) sdf[out_index ? (int64_t)out_index[row] : row] = f;
   if (d7) {
-    float coef = 1.f - f * f;
+    float coef = unit_seed ? 1.f : 1.f - f * f;
     for (int c = lane; c < HM_HIDDEN; c += 32) d7[row * HM_HIDDEN + c] = (h[c] > 0.f) ? coef * w8[c] : 0.f;
   }
 }
@@ -158,6 +160,7 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
     HM_CUDA(cudaStreamSynchronize(st));
     n_total = nd < rows.n ? nd : rows.n;
   }
+  if (!h_absmax_out) { if (d_jac) ctx->counters.rows_jacobian += n_total; else ctx->counters.rows_forward += n_total; }
 
   for (int64_t r0 = 0; r0 < n_total; r0 += CH) {
     int64_t n = n_total - r0 < CH ? n_total - r0 : CH;
@@ -182,7 +185,9 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
       launch_gemm<true>(h[l - 1], HM_HIDDEN, ctx->d_W[l], HM_HIDDEN, ctx->d_b[l], h[l], HM_HIDDEN, n, HM_HIDDEN, HM_HIDDEN,
                         epi, x0, HM_IN, st);
     }
-    head_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h[7], ctx->d_W[8], ctx->d_b[8], n, d_sdf + r0, want_jac ? dA : nullptr);
+    head_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h[7], ctx->d_W[8], ctx->d_b[8], n, rows.d_out_index ? d_sdf : d_sdf + r0,
+                                                         rows.d_out_index ? rows.d_out_index + r0 : nullptr, want_jac ? dA : nullptr,
+                                                         h_absmax_out ? 1 : 0);
     if (!want_jac) continue;
     // backward to the input (what autograd.grad computes for utils.py:112-122)
     float* cur = dA;

@@ -10,7 +10,9 @@
 // scan/scatter (compaction of the in-band samples) -> decoder forward+Jacobian (recon points +
 // in-band samples) -> ray / point Jacobians -> normal-equation partials -> per-fruit solve + update.
 // All reductions are order-deterministic (no floating-point atomics).
+#include <limits.h>
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -79,8 +81,9 @@ __device__ double inv23(const float* Tf) {
 // ---------------------------------------------------------------------------------------------
 __global__ void frame_setup_kernel(int n_frames, FrameState* __restrict__ fs, const float* __restrict__ T_ow,
                                    const float* __restrict__ T_wc, const float* __restrict__ cube_radius,
-                                   const uint8_t* __restrict__ active, int M) {
+                                   const uint8_t* __restrict__ active, int M, int32_t* __restrict__ n_valid_total) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) *n_valid_total = 0;            // the sample kernel of this iteration compacts the in-sphere samples from slot 0
   if (g >= n_frames) return;
   FrameState& F = fs[g];
   F.valid_count = 0;
@@ -113,31 +116,57 @@ __global__ void frame_setup_kernel(int n_frames, FrameState* __restrict__ fs, co
 // ---------------------------------------------------------------------------------------------
 // loss.py:30-40: sample points on the rays, camera -> object, in-sphere test
 // ---------------------------------------------------------------------------------------------
-__global__ void sample_kernel(int64_t n_samples, int M, FrameState* __restrict__ fs, const int32_t* __restrict__ ray_frame,
-                              const float* __restrict__ rays, const uint8_t* __restrict__ active, float* __restrict__ xyz,
-                              uint8_t* __restrict__ valid) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_samples) return;
-  int64_t r = i / M;
-  int m = (int)(i % M);
-  int g = ray_frame[r];
-  const FrameState& F = fs[g];
-  if (!active[F.fruit]) { valid[i] = 0; return; }
-  float d = F.depths[m];
-  float cx = __fmul_rn(rays[r * 3 + 0], d), cy = __fmul_rn(rays[r * 3 + 1], d), cz = __fmul_rn(rays[r * 3 + 2], d);
-  float p[3];
+// The in-sphere samples are COMPACTED here for the decoder (the reference decodes only them, loss.py:47-49): a warp-aggregated
+// integer atomic hands out slots, so the compact order varies from run to run, but every row is evaluated independently of its
+// neighbours and its SDF is written back to the sample's own position (idx_c), so the results do not depend on that order.
+__global__ void __launch_bounds__(256) sample_kernel(int64_t n_samples, int M, FrameState* __restrict__ fs, const int32_t* __restrict__ ray_frame,
+                                                     const float* __restrict__ rays, const uint8_t* __restrict__ active, float* __restrict__ xyz,
+                                                     uint8_t* __restrict__ valid, float* __restrict__ xyz_c, int32_t* __restrict__ idx_c,
+                                                     int32_t* __restrict__ row_latent_c, int32_t* __restrict__ n_valid_total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool v = false;
+  int g = -1, fruit = 0;
+  float p[3] = {0.f, 0.f, 0.f};
+  if (i < n_samples) {
+    const int64_t r = i / M;
+    const int m = (int)(i % M);
+    g = ray_frame[r];
+    const FrameState& F = fs[g];
+    fruit = F.fruit;
+    if (active[fruit]) {
+      const float d = F.depths[m];
+      const float cx = __fmul_rn(rays[r * 3 + 0], d), cy = __fmul_rn(rays[r * 3 + 1], d), cz = __fmul_rn(rays[r * 3 + 2], d);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float s = __fadd_rn(__fadd_rn(__fmul_rn(cx, F.A[k * 3 + 0]), __fmul_rn(cy, F.A[k * 3 + 1])), __fmul_rn(cz, F.A[k * 3 + 2]));
-    p[k] = __fadd_rn(s, F.t[k]);
+      for (int k = 0; k < 3; ++k) {
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(cx, F.A[k * 3 + 0]), __fmul_rn(cy, F.A[k * 3 + 1])), __fmul_rn(cz, F.A[k * 3 + 2]));
+        p[k] = __fadd_rn(s, F.t[k]);
+      }
+      const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2])));
+      v = nrm < F.rho;
+      xyz[i * 3 + 0] = p[0];
+      xyz[i * 3 + 1] = p[1];
+      xyz[i * 3 + 2] = p[2];
+    }
+    valid[i] = v ? 1 : 0;
   }
-  float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2])));
-  bool v = nrm < F.rho;
-  xyz[i * 3 + 0] = p[0];
-  xyz[i * 3 + 1] = p[1];
-  xyz[i * 3 + 2] = p[2];
-  valid[i] = v ? 1 : 0;
-  if (v) atomicAdd(&fs[g].valid_count, 1);    // integer count: order independent
+  const unsigned vm = __ballot_sync(0xffffffffu, v);
+  if (vm == 0u) return;
+  int base = 0;
+  const int leader = __ffs(vm) - 1;
+  if (lane == leader) base = atomicAdd(n_valid_total, __popc(vm));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  // per-frame in-sphere counts (loss.py:38-45): one integer atomic per (warp, frame)
+  const unsigned same = __match_any_sync(0xffffffffu, v ? g : -1 - lane);
+  if (v) {
+    if (lane == __ffs(same) - 1) atomicAdd(&fs[g].valid_count, __popc(same));
+    const int slot = base + __popc(vm & ((1u << lane) - 1u));
+    xyz_c[(int64_t)slot * 3 + 0] = p[0];
+    xyz_c[(int64_t)slot * 3 + 1] = p[1];
+    xyz_c[(int64_t)slot * 3 + 2] = p[2];
+    idx_c[slot] = (int32_t)i;
+    row_latent_c[slot] = fruit;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -506,7 +535,7 @@ __device__ void exp_pose(const float* x, int pose_dim, float* T /*16*/) {
 
 // ---------------------------------------------------------------------------------------------
 // optimizer.py:200-291: assemble H, b from the partials, LM damping, solve, exp-map update, stop tests.
-// One block (64 threads) per fruit; the 39x39 solve runs in fp64 (Gaussian elimination, partial pivoting).
+// One block per fruit; the 39x39 solve runs in fp64 (Gauss-Jordan elimination with partial pivoting, one matrix element per thread).
 // ---------------------------------------------------------------------------------------------
 struct SolveArgs {
   const int32_t* fruit_block_begin;   // [n_fruits + 1] blocks of fruit f (sorted by fruit, then term)
@@ -526,37 +555,40 @@ struct SolveArgs {
   int joint, iter, iter_first, iter_last;
 };
 
-__global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
+constexpr int kSolveThreads = 1024;      // 32 x 32: thread (ty, tx) owns the elements (ty + 32 i, tx + 32 j) of the augmented system
+
+__global__ void __launch_bounds__(kSolveThreads) solve_kernel(SolveArgs a, DevParams P) {
   const int f = blockIdx.x;
   if (!a.active[f]) return;
   const int est = a.joint ? P.est : HM_LATENT;
   const int pd = a.joint ? P.pose_dim : 0;
   const int tri = est * (est + 1) / 2;
-  __shared__ double sH[kE][kE + 2];      // augmented [H | b]; the row stride of 41 doubles keeps the per-row accesses of the
-                                         // elimination (one row per thread) off the same banks (40 would be a 16-way conflict)
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  __shared__ double sH[kE][kE + 2];      // augmented [H | b]; the odd row stride keeps column accesses off a single bank
   __shared__ double sAcc[3][kPartial];
-  __shared__ double s_dx[kE];
   __shared__ int s_n[3];
+  __shared__ int s_piv, s_fail;
   const int b0 = a.fruit_block_begin[f], b1 = a.fruit_block_begin[f + 1];
   // The blocks of a fruit are sorted by term: find the three ranges once, so that the sums below are plain loops whose loads
-  // are independent of each other (a term test per block made every load wait for the previous one).
+  // are independent of each other.
   __shared__ int s_tb[4];                // blocks [s_tb[t], s_tb[t + 1]) carry term t
-  if (threadIdx.x < 4) s_tb[threadIdx.x] = (threadIdx.x == 0) ? b0 : b1;
+  if (tid < 4) s_tb[tid] = (tid == 0) ? b0 : b1;
+  if (tid == 0) s_fail = 0;
   __syncthreads();
-  for (int b = b0 + 1 + (int)threadIdx.x; b < b1; b += 64) {
+  for (int b = b0 + 1 + tid; b < b1; b += kSolveThreads) {
     const int t0 = a.blocks[b - 1].term, t1 = a.blocks[b].term;
     for (int t = t0 + 1; t <= t1; ++t) s_tb[t] = b;          // first block of term t (and of any empty term before it)
   }
   __syncthreads();
-  if (threadIdx.x == 0 && b1 > b0) {                          // terms missing at the front / back of the range
+  if (tid == 0 && b1 > b0) {                                  // terms missing at the front / back of the range
     const int first = a.blocks[b0].term, last = a.blocks[b1 - 1].term;
     for (int t = 1; t <= first; ++t) s_tb[t] = b0;
     for (int t = last + 1; t < 3; ++t) s_tb[t] = b1;
   }
   __syncthreads();
-  // fixed-order sum of the block partials per term (the latent-only loop has the recon term only)
+  // fixed-order fp64 sum of the block partials per term (the latent-only loop has the recon term only)
   const int term_lo = a.joint ? 0 : 2;
-  for (int e = threadIdx.x + term_lo * (tri + est); e < 3 * (tri + est); e += 64) {
+  for (int e = tid + term_lo * (tri + est); e < 3 * (tri + est); e += kSolveThreads) {
     const int term = e / (tri + est), idx = e % (tri + est);
     const int tb0 = s_tb[term], tb1 = s_tb[term + 1];
     double acc = 0.0;
@@ -564,24 +596,22 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
     for (int b = tb0; b < tb1; ++b) acc += (double)a.partials[(size_t)b * kPartial + idx];
     sAcc[term][idx] = acc;
   }
-  if (threadIdx.x < 3) {
+  if (tid < 3) {
     int n = 0;
-    for (int b = s_tb[threadIdx.x]; b < s_tb[threadIdx.x + 1]; ++b) n += a.block_items[b];
-    s_n[threadIdx.x] = n;
+    for (int b = s_tb[tid]; b < s_tb[tid + 1]; ++b) n += a.block_items[b];
+    s_n[tid] = n;
   }
   __syncthreads();
   const int n_d = s_n[0], n_r = s_n[2];
-  if (a.joint && n_d == 0) {                      // optimizer.py:139-141 "This submap is not valid"
-    if (threadIdx.x == 0) { a.active[f] = 0; atomicOr(&a.status[f], HM_STATUS_SUBMAP_INVALID); }
-    return;
-  }
-  if (n_r == 0) {                                  // no surface points: nothing to optimise (the reference would fail on empty input)
-    if (threadIdx.x == 0) { a.active[f] = 0; atomicOr(&a.status[f], HM_STATUS_SUBMAP_INVALID); }
+  if ((a.joint && n_d == 0) || n_r == 0) {
+    // optimizer.py:139-141 "This submap is not valid" (no ray survived) / no surface points: nothing to optimise (the reference
+    // would fail on the empty tensor)
+    if (tid == 0) { a.active[f] = 0; atomicOr(&a.status[f], HM_STATUS_SUBMAP_INVALID); }
     return;
   }
   const double wd = a.joint ? P.w_depth / (double)n_d : 0.0, wm = a.joint ? P.w_mask / (double)n_d : 0.0, wr = P.w_recon / (double)n_r;
   float* lat = a.latents + (size_t)f * HM_LATENT;
-  for (int e = threadIdx.x; e < tri + est; e += 64) {
+  for (int e = tid; e < tri + est; e += kSolveThreads) {
     double v = a.joint ? wd * sAcc[0][e] + wm * sAcc[1][e] + wr * sAcc[2][e] : wr * sAcc[2][e];   // (terms 0, 1 are not summed when !joint)
     if (e < tri) {
       int r = 0, rem = e;
@@ -594,40 +624,40 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int c = 0; c < HM_LATENT; ++c) {          // code regulariser (:200-203)
-      sH[pd + c][pd + c] += P.w_codereg;
-      sH[pd + c][est] += -P.w_codereg * (double)lat[c];
-    }
-    if (a.joint && P.scale_on) sH[pd - 1][pd - 1] += P.s_damp;     // :217-218
-    if (P.lm_on) {                                                  // :220-225
-      if (P.lm_eye) {
-        double mx = sH[0][0];
-        for (int i = 1; i < est; ++i) mx = fmax(mx, sH[i][i]);
-        for (int i = 0; i < est; ++i) sH[i][i] += P.lm_lambda_0 * mx;
-      } else {
-        for (int i = 0; i < est; ++i) sH[i][i] += P.lm_lambda_0 * sH[i][i];
-      }
-    }
+  if (tid < HM_LATENT) {                            // code regulariser (:200-203)
+    sH[pd + tid][pd + tid] += P.w_codereg;
+    sH[pd + tid][est] += -P.w_codereg * (double)lat[tid];
   }
+  if (tid == 32 && a.joint && P.scale_on) sH[pd - 1][pd - 1] += P.s_damp;     // :217-218
   __syncthreads();
+  if (P.lm_on) {                                                              // :220-225
+    if (P.lm_eye) {
+      double mx = sH[0][0];
+      for (int i = 1; i < est; ++i) mx = fmax(mx, sH[i][i]);
+      __syncthreads();
+      if (tid < est) sH[tid][tid] += P.lm_lambda_0 * mx;
+    } else if (tid < est) {
+      sH[tid][tid] += P.lm_lambda_0 * sH[tid][tid];
+    }
+    __syncthreads();
+  }
   if (a.last_H) {
-    for (int e = threadIdx.x; e < est * est; e += 64) a.last_H[(size_t)f * kE * kE + e] = (float)sH[e / est][e % est];
-    for (int e = threadIdx.x; e < est; e += 64) a.last_b[(size_t)f * kE + e] = (float)sH[e][est];
+    for (int e = tid; e < est * est; e += kSolveThreads) a.last_H[(size_t)f * kE * kE + e] = (float)sH[e / est][e % est];
+    if (tid < est) a.last_b[(size_t)f * kE + tid] = (float)sH[tid][est];
   }
   double bmax = 0.0;
-  if (threadIdx.x == 0)
+  if (tid == 0)
     for (int i = 0; i < est; ++i) bmax = fmax(bmax, fabs((double)(float)sH[i][est]));
   __syncthreads();
-  // Gaussian elimination with partial pivoting on [H | b] (delta_x = H^-1 b, :234)
+  // delta_x = H^-1 b (:234): Gauss-Jordan elimination with partial pivoting on [H | b] in fp64, one element per thread.  Step k
+  // reads row k and column k and writes neither (column k of the other rows is simply never read again), so one barrier
+  // separates the steps.
   for (int k = 0; k < est; ++k) {
-    __shared__ int s_piv;
-    if (threadIdx.x < 32) {
-      // arg max_i |H[i][k]|, i >= k, the FIRST maximum on ties (what a serial scan with '>' finds): lanes cover rows
-      // i = k + lane and k + lane + 32 (est <= 39), then a shuffle reduction on (value, index)
+    if (tid < 32) {
+      // arg max_i |H[i][k]|, i >= k, the FIRST maximum on ties: lanes cover rows k + lane and k + lane + 32 (est <= 39)
       double best = -1.0;
       int p = est;
-      for (int i = k + (int)threadIdx.x; i < est; i += 32) {
+      for (int i = k + tid; i < est; i += 32) {
         const double v = fabs(sH[i][k]);
         if (v > best) { best = v; p = i; }
       }
@@ -637,30 +667,39 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
         const int op = __shfl_xor_sync(0xffffffffu, p, off);
         if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
       }
-      if (threadIdx.x == 0) s_piv = p;
+      if (tid == 0) {
+        s_piv = p;
+        if (!(best > 0.0) || !isfinite(best)) s_fail = 1;          // singular or non-finite system
+      }
     }
     __syncthreads();
+    if (s_fail) break;
     const int p = s_piv;
-    if (p != k)
-      for (int c = threadIdx.x; c <= est; c += 64) { double t = sH[k][c]; sH[k][c] = sH[p][c]; sH[p][c] = t; }
+    if (p != k && ty == 0)
+      for (int c = tx; c <= est; c += 32) { const double t = sH[k][c]; sH[k][c] = sH[p][c]; sH[p][c] = t; }
     __syncthreads();
     const double piv = sH[k][k];
-    for (int i = k + 1 + threadIdx.x; i < est; i += 64) {
+    for (int i = ty; i < est; i += 32) {
+      if (i == k) continue;
       const double m = sH[i][k] / piv;
-      for (int c = k; c <= est; ++c) sH[i][c] -= m * sH[k][c];
+      for (int c = tx; c <= est; c += 32)
+        if (c > k) sH[i][c] -= m * sH[k][c];
     }
     __syncthreads();
   }
-  // back substitution, column oriented: once dx[i] is known every row above it subtracts its term (one row per thread)
-  for (int i = est - 1; i >= 0; --i) {
-    if (threadIdx.x == 0) s_dx[i] = sH[i][est] / sH[i][i];
-    __syncthreads();
-    if ((int)threadIdx.x < i) sH[threadIdx.x][est] -= sH[threadIdx.x][i] * s_dx[i];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     float dx[kE];
-    for (int i = 0; i < est; ++i) dx[i] = (float)s_dx[i];
+    bool bad = s_fail != 0;
+    for (int i = 0; i < est && !bad; ++i) {
+      dx[i] = (float)(sH[i][est] / sH[i][i]);
+      if (!isfinite(dx[i])) bad = true;
+    }
+    if (bad) {
+      // torch.inverse raises on a singular matrix; here the fruit stops with its state untouched and a status bit
+      atomicOr(&a.status[f], HM_STATUS_SOLVE_FAILED);
+      a.active[f] = 0;
+      return;
+    }
     if (a.last_dx) for (int i = 0; i < est; ++i) a.last_dx[(size_t)f * kE + i] = dx[i];
     int st = 0;
     float delta_tran = 0.f, delta_rot = 0.f, delta_scale = 0.f;
@@ -703,15 +742,11 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a, DevParams P) {
 }
 
 
-// The tensor-core decoder counts the launches in which an fp16 operand conversion saturated (flags[0]).  After the loop that
-// count is turned into HM_STATUS_F16_SATURATED on every fruit of the batch (the fruit cannot be attributed) and reset.
-__global__ void saturation_status_kernel(int32_t* __restrict__ flags, int n_fruits, int32_t* __restrict__ status) {
-  const int sat = flags[0];
-  __syncthreads();
-  if (sat != 0)
-    for (int f = threadIdx.x; f < n_fruits; f += blockDim.x) atomicOr(&status[f], HM_STATUS_F16_SATURATED);
-  __syncthreads();
-  if (threadIdx.x == 0) flags[0] = 0;
+// The tensor-core decoder marks the fruits (latent-table rows) one of whose rows left the calibrated fp16 range during the loop;
+// after the loop the marks become HM_STATUS_F16_SATURATED on exactly those fruits.
+__global__ void saturation_status_kernel(const int32_t* __restrict__ fruit_sat, int n_fruits, int32_t* __restrict__ status) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < n_fruits && fruit_sat[f] != 0) atomicOr(&status[f], HM_STATUS_F16_SATURATED);
 }
 
 // host helpers ---------------------------------------------------------------------------------
@@ -758,6 +793,34 @@ inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 }  // namespace
 
+// per-call tables built on the device (O(rays) / O(points) work that used to be host loops + uploads)
+__global__ void ray_table_kernel(const FrameState* __restrict__ fs, int32_t* __restrict__ ray_frame) {
+  const int g = blockIdx.x;
+  const int64_t r0 = fs[g].ray_begin;
+  const int n = fs[g].n_rays;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) ray_frame[r0 + j] = g;
+}
+__global__ void point_table_kernel(const int64_t* __restrict__ point_offsets, int32_t* __restrict__ point_fruit) {
+  const int f = blockIdx.x;
+  const int64_t i1 = point_offsets[f + 1];
+  for (int64_t i = point_offsets[f] + threadIdx.x; i < i1; i += blockDim.x) point_fruit[i] = f;
+}
+
+// Pinned staging arena of the per-call host tables: the uploads are asynchronous on the caller's stream and the arena is only
+// rewritten after the previous call's uploads have completed (event), so hm_optimize_* never waits for queued GPU work.
+static int stage_reserve(hm_context* ctx, size_t bytes) {
+  if (ctx->stage_event) HM_CUDA(cudaEventSynchronize(ctx->stage_event));
+  else HM_CUDA(cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
+  if (bytes <= ctx->stage_bytes) return HM_OK;
+  if (ctx->h_stage) HM_CUDA(cudaFreeHost(ctx->h_stage));
+  ctx->h_stage = nullptr;
+  ctx->stage_bytes = 0;
+  bytes = (bytes + 65535) & ~size_t(65535);
+  HM_CUDA(cudaMallocHost(&ctx->h_stage, bytes));
+  ctx->stage_bytes = bytes;
+  return HM_OK;
+}
+
 int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* b, bool joint, cudaStream_t st) {
   HM_CHECK(ctx && p && b, "hm_optimize: null argument");
   HM_CHECK(b->n_fruits > 0 && b->d_latents && b->d_T_ow && b->d_points_w && b->h_point_offsets && b->d_iter_count && b->d_status,
@@ -766,6 +829,7 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
   HM_CUDA(cudaSetDevice(ctx->device));
   const int nf = b->n_fruits;
   const int64_t n_points = b->h_point_offsets[nf];
+  HM_CHECK(n_points >= 0 && b->h_point_offsets[0] == 0, "hm_optimize: point offsets must start at 0 and be non-decreasing");
   int n_frames = 0;
   int64_t n_rays = 0;
   const int M = p->n_depth_samples;
@@ -781,16 +845,37 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
   const int est = pose_dim + HM_LATENT;
   const int64_t S = n_rays * M;
   const int64_t Gmax = n_points + S;
+  HM_CHECK(Gmax < (int64_t)INT32_MAX - 64, "hm_optimize: %lld decoder rows per iteration exceed the int32 row index of one call; split the batch",
+           (long long)Gmax);
   const int n_scan_blocks = (int)((n_rays + 255) / 256);
 
-  // ---- host-side static tables
-  std::vector<FrameState> h_fs(n_frames);
-  std::vector<int32_t> h_ray_frame(n_rays), h_point_fruit(n_points), h_row_latent_s;
-  std::vector<RedBlock> h_blocks;
-  std::vector<int32_t> h_fbb(nf + 1);
-  if (joint) h_row_latent_s.resize(S);
+  // ---- small host-side tables (per frame / per normal-equation block), staged in pinned memory
+  int n_blocks = 0;
   for (int f = 0; f < nf; ++f) {
-    h_fbb[f] = (int)h_blocks.size();
+    if (joint && b->h_frame_offsets[f + 1] > b->h_frame_offsets[f]) {
+      const int64_t nr = b->h_ray_offsets[b->h_frame_offsets[f + 1]] - b->h_ray_offsets[b->h_frame_offsets[f]];
+      n_blocks += 2 * (int)((nr + kRedItems - 1) / kRedItems);
+    }
+    n_blocks += (int)((b->h_point_offsets[f + 1] - b->h_point_offsets[f] + kRedItems - 1) / kRedItems);
+  }
+  Carver hs_size(nullptr);
+  hs_size.take<FrameState>(n_frames); hs_size.take<RedBlock>(n_blocks); hs_size.take<int32_t>(nf + 1); hs_size.take<int64_t>(nf + 1);
+  hs_size.take<float>(nf); hs_size.take<uint8_t>(nf);
+  int rc = stage_reserve(ctx, hs_size.off + 256);
+  if (rc) return rc;
+  Carver hs(ctx->h_stage);
+  FrameState* h_fs = hs.take<FrameState>(n_frames);
+  RedBlock* h_blocks = hs.take<RedBlock>(n_blocks);
+  int32_t* h_fbb = hs.take<int32_t>(nf + 1);
+  int64_t* h_po = hs.take<int64_t>(nf + 1);
+  float* h_cr = hs.take<float>(nf);
+  uint8_t* h_pk = hs.take<uint8_t>(nf);
+  int nb = 0;
+  for (int f = 0; f < nf; ++f) {
+    h_fbb[f] = nb;
+    h_po[f] = b->h_point_offsets[f];
+    h_cr[f] = joint ? b->h_cube_radius[f] : 0.f;
+    h_pk[f] = joint ? b->h_pose_known[f] : 0;
     if (joint) {
       int64_t rb = -1, re = -1;
       for (int g = b->h_frame_offsets[f]; g < b->h_frame_offsets[f + 1]; ++g) {
@@ -800,53 +885,51 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
         F.n_fg = b->h_n_fg[g];
         F.ray_begin = b->h_ray_offsets[g];
         F.n_rays = (int32_t)(b->h_ray_offsets[g + 1] - b->h_ray_offsets[g]);
-        for (int64_t r = b->h_ray_offsets[g]; r < b->h_ray_offsets[g + 1]; ++r) {
-          h_ray_frame[r] = g;
-          for (int m = 0; m < M; ++m) h_row_latent_s[r * M + m] = f;
-        }
         if (rb < 0) rb = b->h_ray_offsets[g];
         re = b->h_ray_offsets[g + 1];
       }
       for (int term = 0; term < 2; ++term)
         for (int64_t s0 = rb; rb >= 0 && s0 < re; s0 += kRedItems)
-          h_blocks.push_back({f, term, s0, (int)std::min<int64_t>(kRedItems, re - s0)});
+          h_blocks[nb++] = {f, term, s0, (int)std::min<int64_t>(kRedItems, re - s0)};
     }
-    for (int64_t i = b->h_point_offsets[f]; i < b->h_point_offsets[f + 1]; ++i) h_point_fruit[i] = f;
     for (int64_t s0 = b->h_point_offsets[f]; s0 < b->h_point_offsets[f + 1]; s0 += kRedItems)
-      h_blocks.push_back({f, 2, s0, (int)std::min<int64_t>(kRedItems, b->h_point_offsets[f + 1] - s0)});
+      h_blocks[nb++] = {f, 2, s0, (int)std::min<int64_t>(kRedItems, b->h_point_offsets[f + 1] - s0)};
   }
-  h_fbb[nf] = (int)h_blocks.size();
-  const int n_blocks = (int)h_blocks.size();
+  h_fbb[nf] = nb;
+  h_po[nf] = n_points;
+  HM_CHECK(nb == n_blocks, "hm_optimize: internal block count mismatch");
 
   // ---- carve the workspace (two passes: size, then pointers)
   struct Ptrs {
-    FrameState* fs; int32_t *ray_frame, *point_fruit, *row_latent_s, *fbb; RedBlock* blocks; float* cube_radius; uint8_t *pose_known, *active;
+    FrameState* fs; int32_t *ray_frame, *point_fruit, *fbb; int64_t* point_offsets; RedBlock* blocks; float* cube_radius; uint8_t *pose_known, *active;
     float *xyz_s, *sdf_s, *coef_e, *coef_m; uint8_t* valid; unsigned long long* ray_mask; float *res_d, *res_m;
+    float* xyz_c; int32_t *idx_c, *row_latent_c, *n_valid;
     int32_t *ray_k, *ray_off, *ray_slot, *block_sum, *block_base, *n_rows_dyn;
-    float *xyz_g, *sdf_g, *jac_g; int32_t* row_latent_g; float *J_d, *J_m, *J_r, *res_r, *partials; int32_t* block_items;
+    float *xyz_g, *sdf_g, *jac_g; int32_t* row_latent_g; float *J_d, *J_m, *J_r, *res_r, *partials; int32_t *block_items, *fruit_sat;
   } w;
   auto carve = [&](void* base) {
     Carver c(base);
     w.fs = c.take<FrameState>(n_frames); w.ray_frame = c.take<int32_t>(n_rays); w.point_fruit = c.take<int32_t>(n_points);
-    w.row_latent_s = c.take<int32_t>(S); w.fbb = c.take<int32_t>(nf + 1); w.blocks = c.take<RedBlock>(n_blocks);
+    w.fbb = c.take<int32_t>(nf + 1); w.point_offsets = c.take<int64_t>(nf + 1); w.blocks = c.take<RedBlock>(n_blocks);
     w.cube_radius = c.take<float>(nf); w.pose_known = c.take<uint8_t>(nf); w.active = c.take<uint8_t>(nf);
     w.xyz_s = c.take<float>(S * 3); w.sdf_s = c.take<float>(S); w.coef_e = c.take<float>(S); w.coef_m = c.take<float>(S);
     w.valid = c.take<uint8_t>(S); w.ray_mask = c.take<unsigned long long>(n_rays); w.res_d = c.take<float>(n_rays); w.res_m = c.take<float>(n_rays);
+    w.xyz_c = c.take<float>(S * 3); w.idx_c = c.take<int32_t>(S); w.row_latent_c = c.take<int32_t>(S); w.n_valid = c.take<int32_t>(4);
     w.ray_k = c.take<int32_t>(n_rays); w.ray_off = c.take<int32_t>(n_rays); w.ray_slot = c.take<int32_t>(n_rays);
     w.block_sum = c.take<int32_t>(n_scan_blocks + 1); w.block_base = c.take<int32_t>(n_scan_blocks + 1); w.n_rows_dyn = c.take<int32_t>(4);
     w.xyz_g = c.take<float>(Gmax * 3); w.sdf_g = c.take<float>(Gmax); w.jac_g = c.take<float>(Gmax * HM_IN); w.row_latent_g = c.take<int32_t>(Gmax);
     w.J_d = c.take<float>(n_rays * kE); w.J_m = c.take<float>(n_rays * kE); w.J_r = c.take<float>(n_points * kE); w.res_r = c.take<float>(n_points);
-    w.partials = c.take<float>((size_t)n_blocks * kPartial); w.block_items = c.take<int32_t>(n_blocks);
+    w.partials = c.take<float>((size_t)n_blocks * kPartial); w.block_items = c.take<int32_t>(n_blocks); w.fruit_sat = c.take<int32_t>(nf);
     return c.off + 256;
   };
   const size_t need = carve(nullptr);
-  int rc = hm_ws2_reserve(ctx, need);
+  rc = hm_ws2_reserve(ctx, need);
   if (rc) return rc;
   carve(ctx->ws2);
 
   // last-system buffers (test hook)
   if (ctx->last_n_fruits < nf) {
-    if (ctx->d_last_H) { cudaFree(ctx->d_last_H); cudaFree(ctx->d_last_b); cudaFree(ctx->d_last_dx); }
+    if (ctx->d_last_H) { HM_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->d_last_H); cudaFree(ctx->d_last_b); cudaFree(ctx->d_last_dx); }
     HM_CUDA(cudaMalloc(&ctx->d_last_H, sizeof(float) * (size_t)nf * kE * kE));
     HM_CUDA(cudaMalloc(&ctx->d_last_b, sizeof(float) * (size_t)nf * kE));
     HM_CUDA(cudaMalloc(&ctx->d_last_dx, sizeof(float) * (size_t)nf * kE));
@@ -854,23 +937,22 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
   }
   ctx->last_est = est;
 
-  // ---- upload static tables
-  std::vector<float> h_cr(nf, 0.f);
-  std::vector<uint8_t> h_pk(nf, 0), h_act(nf, 1);
-  if (joint) for (int f = 0; f < nf; ++f) { h_cr[f] = b->h_cube_radius[f]; h_pk[f] = b->h_pose_known[f]; }
+  // ---- upload the staged tables, build the O(rays) / O(points) tables on the device
   auto up = [&](void* d, const void* h, size_t bytes) -> cudaError_t { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
-  HM_CUDA(up(w.fs, h_fs.data(), sizeof(FrameState) * n_frames));
-  HM_CUDA(up(w.ray_frame, h_ray_frame.data(), sizeof(int32_t) * n_rays));
-  HM_CUDA(up(w.point_fruit, h_point_fruit.data(), sizeof(int32_t) * n_points));
-  HM_CUDA(up(w.row_latent_s, h_row_latent_s.data(), sizeof(int32_t) * S));
-  HM_CUDA(up(w.fbb, h_fbb.data(), sizeof(int32_t) * (nf + 1)));
-  HM_CUDA(up(w.blocks, h_blocks.data(), sizeof(RedBlock) * n_blocks));
-  HM_CUDA(up(w.cube_radius, h_cr.data(), sizeof(float) * nf));
-  HM_CUDA(up(w.pose_known, h_pk.data(), nf));
-  HM_CUDA(up(w.active, h_act.data(), nf));
+  HM_CUDA(up(w.fs, h_fs, sizeof(FrameState) * n_frames));
+  HM_CUDA(up(w.blocks, h_blocks, sizeof(RedBlock) * n_blocks));
+  HM_CUDA(up(w.fbb, h_fbb, sizeof(int32_t) * (nf + 1)));
+  HM_CUDA(up(w.point_offsets, h_po, sizeof(int64_t) * (nf + 1)));
+  HM_CUDA(up(w.cube_radius, h_cr, sizeof(float) * nf));
+  HM_CUDA(up(w.pose_known, h_pk, nf));
+  HM_CUDA(cudaEventRecord(ctx->stage_event, st));
+  HM_CUDA(cudaMemsetAsync(w.active, 1, nf, st));
+  HM_CUDA(cudaMemsetAsync(w.fruit_sat, 0, sizeof(int32_t) * nf, st));
   HM_CUDA(cudaMemsetAsync(b->d_iter_count, 0, sizeof(int32_t) * nf, st));
   HM_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int32_t) * nf, st));
-  HM_CUDA(cudaStreamSynchronize(st));      // the host vectors above go out of scope; nothing below syncs
+  int64_t launches = 0;
+  if (n_frames > 0) { ray_table_kernel<<<n_frames, 128, 0, st>>>(w.fs, w.ray_frame); ++launches; }
+  if (n_points > 0) { point_table_kernel<<<nf, 256, 0, st>>>(w.point_offsets, w.point_fruit); ++launches; }
 
   SolveArgs sa;
   sa.fruit_block_begin = w.fbb; sa.blocks = w.blocks; sa.partials = w.partials; sa.block_items = w.block_items;
@@ -879,14 +961,18 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
   sa.last_H = ctx->d_last_H; sa.last_b = ctx->d_last_b; sa.last_dx = ctx->d_last_dx;
   sa.joint = joint ? 1 : 0; sa.iter_first = p->iter_offset; sa.iter_last = p->iter_offset + p->max_iter - 1;
 
-  int64_t launches = 0;
   for (int it = p->iter_offset; it < p->iter_offset + p->max_iter; ++it) {
     hm_rows grows = {nullptr, w.xyz_g, b->d_latents, w.row_latent_g, n_points, nullptr};
+    grows.d_latent_sat = w.fruit_sat;
     if (joint && n_rays > 0) {
-      frame_setup_kernel<<<nblk(n_frames, 64), 64, 0, st>>>(n_frames, w.fs, b->d_T_ow, b->d_T_wc, w.cube_radius, w.active, M);
-      sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, b->d_rays, w.active, w.xyz_s, w.valid);
+      frame_setup_kernel<<<nblk(n_frames, 64), 64, 0, st>>>(n_frames, w.fs, b->d_T_ow, b->d_T_wc, w.cube_radius, w.active, M, w.n_valid);
+      sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, b->d_rays, w.active, w.xyz_s, w.valid, w.xyz_c, w.idx_c,
+                                                  w.row_latent_c, w.n_valid);
       launches += 2;
-      hm_rows srows = {nullptr, w.xyz_s, b->d_latents, w.row_latent_s, S, nullptr};
+      // forward pass over the in-sphere samples only (loss.py:47-49); the SDF of compact row j lands at sample idx_c[j]
+      hm_rows srows = {nullptr, w.xyz_c, b->d_latents, w.row_latent_c, S, w.n_valid};
+      srows.d_out_index = w.idx_c;
+      srows.d_latent_sat = w.fruit_sat;
       rc = hm_decode(ctx, srows, w.sdf_s, nullptr, st);
       if (rc) return rc;
       composite_kernel<<<n_scan_blocks, 256, 0, st>>>(n_rays, P, w.fs, w.ray_frame, b->d_depth_obs, w.valid, w.sdf_s, w.active, w.coef_e,
@@ -898,7 +984,10 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
       grows.n = Gmax;
       grows.d_n_dynamic = w.n_rows_dyn;
     }
-    transform_points_kernel<<<nblk(n_points, 256), 256, 0, st>>>(n_points, w.point_fruit, b->d_points_w, b->d_T_ow, w.xyz_g, w.row_latent_g);
+    if (n_points > 0) {
+      transform_points_kernel<<<nblk(n_points, 256), 256, 0, st>>>(n_points, w.point_fruit, b->d_points_w, b->d_T_ow, w.xyz_g, w.row_latent_g);
+      ++launches;
+    }
     rc = hm_decode(ctx, grows, w.sdf_g, w.jac_g, st);
     if (rc) return rc;
     if (joint && n_rays > 0) {
@@ -906,22 +995,25 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
       ++launches;
     }
     if (joint) {
-      point_jacobian_kernel<<<nblk(n_points, 128), 128, 0, st>>>(n_points, pose_dim, w.xyz_g, w.sdf_g, w.jac_g, w.res_r, w.J_r);
-      normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.J_r, w.res_r, kE, w.active,
-                                                 w.partials, w.block_items);
-      ++launches;
-    } else {
+      if (n_points > 0) {
+        point_jacobian_kernel<<<nblk(n_points, 128), 128, 0, st>>>(n_points, pose_dim, w.xyz_g, w.sdf_g, w.jac_g, w.res_r, w.J_r);
+        ++launches;
+      }
+      if (n_blocks > 0)
+        normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.J_r, w.res_r, kE, w.active,
+                                                   w.partials, w.block_items);
+    } else if (n_blocks > 0) {
       // latent only (optimizer.py:306-429): J = d sdf / d latent = the first 32 columns of the decoder's Jacobian rows and the
       // residual is the SDF itself (loss.py:219-243 with the pose fixed) -- read both where the decoder wrote them
       normal_eq_kernel<<<n_blocks, 128, 0, st>>>(w.blocks, est, it, P, w.J_d, w.J_m, w.res_d, w.res_m, w.ray_k, w.jac_g, w.sdf_g, HM_IN, w.active,
                                                  w.partials, w.block_items);
     }
     sa.iter = it;
-    solve_kernel<<<nf, 64, 0, st>>>(sa, P);
-    launches += 3;
+    solve_kernel<<<nf, kSolveThreads, 0, st>>>(sa, P);
+    launches += 2;
   }
   if (ctx->engine == HM_ENGINE_TC && ctx->d_tc_flags) {
-    saturation_status_kernel<<<1, 256, 0, st>>>(ctx->d_tc_flags, nf, b->d_status);
+    saturation_status_kernel<<<nblk(nf, 256), 256, 0, st>>>(w.fruit_sat, nf, b->d_status);
     ++launches;
   }
   HM_CUDA(cudaGetLastError());
@@ -956,13 +1048,14 @@ static int optimize_host(hm_context* ctx, const hm_opt_params* p, const hm_fruit
   const int n_frames = joint ? hb->h_frame_offsets[nf] : 0;
   const int64_t n_rays = (joint && n_frames) ? hb->h_ray_offsets[n_frames] : 0;
   size_t bytes = sizeof(float) * ((size_t)nf * 48 + n_points * 3 + (size_t)n_frames * 16 + n_rays * 4) + sizeof(int32_t) * 2 * nf + 4096;
-  if (bytes > ctx->pinned_bytes) {      // `pinned` doubles as the device-side I/O arena of the host API
-    if (ctx->pinned) cudaFree(ctx->pinned);
-    ctx->pinned = nullptr;
-    HM_CUDA(cudaMalloc(&ctx->pinned, bytes));
-    ctx->pinned_bytes = bytes;
+  if (bytes > ctx->io_arena_bytes) {
+    if (ctx->io_arena) { HM_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->io_arena); }
+    ctx->io_arena = nullptr;
+    ctx->io_arena_bytes = 0;
+    HM_CUDA(cudaMalloc(&ctx->io_arena, bytes));
+    ctx->io_arena_bytes = bytes;
   }
-  Carver c(ctx->pinned);
+  Carver c(ctx->io_arena);
   hm_fruit_batch db = *hb;
   db.d_latents = c.take<float>((size_t)nf * 32);
   db.d_T_ow = c.take<float>((size_t)nf * 16);
@@ -1043,11 +1136,13 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
   const int64_t S = (int64_t)n_rays * M;
   const int n_scan_blocks = (n_rays + 255) / 256;
   struct { FrameState* fs; int32_t *ray_frame, *status, *ray_k, *ray_off, *ray_slot, *block_sum, *block_base, *n_rows_dyn, *row_latent_g;
-           uint8_t *active, *valid; float *xyz_s, *sdf_s, *coef_e, *coef_m, *xyz_g, *sdf_g, *jac_g, *Jd, *Jm; unsigned long long* ray_mask; } w;
+           int32_t *idx_c, *row_latent_c, *n_valid; uint8_t *active, *valid;
+           float *xyz_s, *xyz_c, *sdf_s, *coef_e, *coef_m, *xyz_g, *sdf_g, *jac_g, *Jd, *Jm; unsigned long long* ray_mask; } w;
   auto carve = [&](void* base) {
     Carver c(base);
     w.fs = c.take<FrameState>(1); w.ray_frame = c.take<int32_t>(n_rays); w.status = c.take<int32_t>(4); w.active = c.take<uint8_t>(4);
     w.xyz_s = c.take<float>(S * 3); w.valid = c.take<uint8_t>(S); w.sdf_s = c.take<float>(S); w.coef_e = c.take<float>(S); w.coef_m = c.take<float>(S);
+    w.xyz_c = c.take<float>(S * 3); w.idx_c = c.take<int32_t>(S); w.row_latent_c = c.take<int32_t>(S); w.n_valid = c.take<int32_t>(4);
     w.ray_mask = c.take<unsigned long long>(n_rays); w.ray_k = c.take<int32_t>(n_rays); w.ray_off = c.take<int32_t>(n_rays); w.ray_slot = c.take<int32_t>(n_rays);
     w.block_sum = c.take<int32_t>(n_scan_blocks + 1); w.block_base = c.take<int32_t>(n_scan_blocks + 1); w.n_rows_dyn = c.take<int32_t>(4);
     w.xyz_g = c.take<float>(S * 3); w.sdf_g = c.take<float>(S); w.jac_g = c.take<float>(S * HM_IN); w.row_latent_g = c.take<int32_t>(S);
@@ -1069,9 +1164,11 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
   HM_CUDA(cudaMemsetAsync(w.ray_frame, 0, sizeof(int32_t) * n_rays, st));
   HM_CUDA(cudaMemsetAsync(w.status, 0, 16, st));
   HM_CUDA(cudaMemsetAsync(w.active, 1, 4, st));
+  HM_CUDA(cudaMemsetAsync(w.n_valid, 0, 16, st));
   HM_CUDA(cudaStreamSynchronize(st));
-  sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, d_rays, w.active, w.xyz_s, w.valid);
-  hm_rows srows = {nullptr, w.xyz_s, d_latent, nullptr, S, nullptr};
+  sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, d_rays, w.active, w.xyz_s, w.valid, w.xyz_c, w.idx_c, w.row_latent_c, w.n_valid);
+  hm_rows srows = {nullptr, w.xyz_c, d_latent, nullptr, S, w.n_valid};      // in-sphere samples only (loss.py:47-49)
+  srows.d_out_index = w.idx_c;
   rc = hm_decode(ctx, srows, w.sdf_s, nullptr, st);
   if (rc) return rc;
   composite_kernel<<<n_scan_blocks, 256, 0, st>>>(n_rays, P, w.fs, w.ray_frame, d_depth_obs, w.valid, w.sdf_s, w.active, w.coef_e, w.coef_m,
@@ -1094,3 +1191,51 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
   if (h_n_valid_samples) *h_n_valid_samples = Fo.valid_count;
   return HM_OK;
 }
+
+#ifdef HM_TESTING
+// ---------------------------------------------------------------------------------------------
+// TEST-ONLY exports (libhortimapping_b200_testing.so): the device functions of the LM step evaluated on their own, so that the
+// tests can hold them against the reference's golden vectors directly (tests/golden/misc.npz: exp_sim3 / exp_se3 incl. the
+// quirk branches of utils.py:279-324, Huber weights incl. the exact-zero case of utils.py:327-358).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void debug_exp_pose_kernel(const float* __restrict__ x, int n, int pose_dim, float* __restrict__ T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) exp_pose(x + (size_t)i * 7, pose_dim, T + (size_t)i * 16);
+}
+__global__ void debug_huber_kernel(const float* __restrict__ r, int n, float b, float* __restrict__ w2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w2[i] = huber_w2(r[i], b);
+}
+}  // namespace
+
+// h_x [n][7] (translation, rotation, log-scale; the last entry is ignored for pose_dim 6) -> h_T [n][16]
+extern "C" int hm_debug_exp_pose(hm_context* ctx, const float* h_x, int n, int pose_dim, float* h_T) {
+  HM_CHECK(ctx && h_x && h_T && n > 0 && (pose_dim == 6 || pose_dim == 7), "hm_debug_exp_pose: bad argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  float *dx = nullptr, *dT = nullptr;
+  HM_CUDA(cudaMalloc(&dx, sizeof(float) * 7 * n));
+  HM_CUDA(cudaMalloc(&dT, sizeof(float) * 16 * n));
+  HM_CUDA(cudaMemcpy(dx, h_x, sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
+  debug_exp_pose_kernel<<<(n + 63) / 64, 64>>>(dx, n, pose_dim, dT);
+  HM_CUDA(cudaGetLastError());
+  HM_CUDA(cudaMemcpy(h_T, dT, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dT);
+  return HM_OK;
+}
+
+// squared Huber weights w^2 of residuals h_r [n] with threshold b (what optimizer.py:145-149 multiplies J^T J and J^T r with)
+extern "C" int hm_debug_huber_w2(hm_context* ctx, const float* h_r, int n, float b, float* h_w2) {
+  HM_CHECK(ctx && h_r && h_w2 && n > 0, "hm_debug_huber_w2: bad argument");
+  HM_CUDA(cudaSetDevice(ctx->device));
+  float *dr = nullptr, *dw = nullptr;
+  HM_CUDA(cudaMalloc(&dr, sizeof(float) * n));
+  HM_CUDA(cudaMalloc(&dw, sizeof(float) * n));
+  HM_CUDA(cudaMemcpy(dr, h_r, sizeof(float) * n, cudaMemcpyHostToDevice));
+  debug_huber_kernel<<<(n + 63) / 64, 64>>>(dr, n, b, dw);
+  HM_CUDA(cudaGetLastError());
+  HM_CUDA(cudaMemcpy(h_w2, dw, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(dw);
+  return HM_OK;
+}
+#endif  // HM_TESTING

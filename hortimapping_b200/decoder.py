@@ -56,7 +56,7 @@ class Decoder:
     `.to()` are accepted and are no-ops (the context is bound to its device at construction)."""
 
     def __init__(self, weights: Sequence[np.ndarray], biases: Sequence[np.ndarray], device: Optional[int] = None,
-                 latent_in: Sequence[int] = (4,), specs: Optional[dict] = None):
+                 latent_in: Sequence[int] = (4,), specs: Optional[dict] = None, _library=None):
         if not torch.cuda.is_available():
             raise RuntimeError("hortimapping_b200.Decoder needs a CUDA device (no CPU fallback)")
         if len(weights) != HM_LAYERS or tuple(latent_in) != (4,):
@@ -65,7 +65,7 @@ class Decoder:
         self.device = torch.device("cuda", self.device_index)
         self.specs = specs or {}
         self.training = False
-        L = _lib.lib()
+        L = _library if _library is not None else _lib.lib()      # (_library: the test-only superset build, _testing.py)
         desc = _lib.DecoderDesc()
         desc.n_layers, desc.latent_size, desc.latent_in_layer = HM_LAYERS, HM_LATENT, 4
         self._keep = []
@@ -111,6 +111,10 @@ class Decoder:
     def set_engine(self, engine: str):
         code = {"tc": _lib.HM_ENGINE_TC, "simt": _lib.HM_ENGINE_SIMT}[engine]
         check(self._L.hm_set_engine(self._h, code), "hm_set_engine")
+
+    def set_zero_shortcut(self, on: bool):
+        """Tensor-core engine: skip the MMAs whose A operand is exactly zero (dead lin3); bit-identical results either way."""
+        check(self._L.hm_set_zero_shortcut(self._h, int(bool(on))), "hm_set_zero_shortcut")
 
     def calibrate(self, rows: torch.Tensor):
         rows = _f32c(rows.reshape(-1, HM_IN), self.device)

@@ -105,6 +105,14 @@ class Optimizer(object):
     def _run(self, pk: PackedBatch, latents: torch.Tensor, T_ow: torch.Tensor, params: _lib.OptParams):
         dec = self.decoder
         dev = dec.device
+        # the C ABI takes raw device pointers and updates them in place: anything but contiguous float32 tensors of the right
+        # shape on the decoder's own GPU would be an illegal address or silently corrupted results
+        for name, t, shape in (("latents", latents, (pk.n_fruits, HM_LATENT)), ("T_ow", T_ow, (pk.n_fruits, 4, 4))):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != dev:
+                raise ValueError(f"{name} must be a CUDA tensor on {dev} (got {getattr(t, 'device', type(t))})")
+            if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"{name} must be a contiguous float32 tensor of shape {shape} (got {t.dtype}, {tuple(t.shape)}, "
+                                 f"contiguous={t.is_contiguous()})")
         if getattr(pk, "_dev", None) is None:       # inputs are uploaded once per PackedBatch and stay resident
             t = lambda a: torch.from_numpy(a).to(dev)
             pk._dev = [t(pk.points)] + ([t(pk.T_wc), t(pk.rays), t(pk.depth_obs)] if pk.joint else [])
@@ -129,6 +137,24 @@ class Optimizer(object):
         self._keep = keep
         return iters, status
 
+    def last_system(self, n_fruits: int, joint: bool = True):
+        """Test / diagnostics hook (hm_get_last_system): H (n,est,est), b (n,est), dx (n,est) of the LAST LM iteration run through
+        this decoder's context, est = pose_dim + 32 for the joint loop and 32 for the latent-only loop."""
+        dec = self.decoder
+        est = ((7 if self.opt_cfg["scale_on"] else 6) if joint else 0) + HM_LATENT
+        H = torch.empty(n_fruits, est, est, device=dec.device)
+        b = torch.empty(n_fruits, est, device=dec.device)
+        dx = torch.empty(n_fruits, est, device=dec.device)
+        check(dec._L.hm_get_last_system(dec.handle, H.data_ptr(), b.data_ptr(), dx.data_ptr(), _stream_ptr(dec.device)), "hm_get_last_system")
+        return H, b, dx
+
+    def check_status(self, status: torch.Tensor) -> np.ndarray:
+        """Opt-in synchronising check of a batched call's status words: warns on HM_STATUS_F16_SATURATED, prints the
+        reference's messages for skipped frames / invalid submaps (optimizer.py:130-141).  Returns the words as numpy."""
+        st = status.detach().cpu().numpy()
+        self._report(st)
+        return st
+
     def _report(self, status: np.ndarray):
         if any(int(s) & _lib.STATUS.get("F16_SATURATED", 0x40) for s in status):
             import warnings
@@ -150,8 +176,12 @@ class Optimizer(object):
                                    points_w: Sequence, cube_radius, pose_known=False, iter_offset: int = 0,
                                    max_iter: Optional[int] = None):
         """latents (n,32) and T_ow (n,4,4) are float32 CUDA tensors updated IN PLACE; returns
-        (latents, T_ow, iter_counts int32 tensor, status int32 tensor) without synchronising."""
+        (latents, T_ow, iter_counts int32 tensor, status int32 tensor) without synchronising.  The status words
+        (HM_STATUS_* bits: fp16 saturation, invalid submap, skipped frame, stop reason) are the caller's to inspect --
+        `check_status(status)` does it (synchronises) and prints / warns like the single-fruit calls."""
         n = latents.shape[0]
+        if len(points_w) != n or len(render_datas) != n:
+            raise ValueError(f"{n} latents but {len(points_w)} point clouds / {len(render_datas)} render_data dicts")
         cr = np.broadcast_to(np.asarray(cube_radius, np.float32), (n,))
         pkn = np.broadcast_to(np.asarray(pose_known, bool), (n,))
         pts = [p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p) for p in points_w]
@@ -163,6 +193,8 @@ class Optimizer(object):
     def shape_opt_deepsdf_batch(self, latents: torch.Tensor, T_ow: torch.Tensor, points_w: Sequence, iter_offset: int = 0,
                                 max_iter: Optional[int] = None):
         n = latents.shape[0]
+        if len(points_w) != n:
+            raise ValueError(f"{n} latents but {len(points_w)} point clouds")
         pts = [p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p) for p in points_w]
         pk = PackedBatch(pts, None, 0, np.zeros(n, np.float32), np.zeros(n, bool))
         params = opt_params_from_cfg(self.opt_cfg, iter_offset, max_iter)

@@ -82,24 +82,29 @@ def _look_at(cam_pos: np.ndarray, target: np.ndarray) -> np.ndarray:
 
 
 def sphere_trace(sdf_jac: SdfJac, latent: np.ndarray, T_oc: np.ndarray, dirs: np.ndarray,
-                 obj_scale: float, steps: int = 64):
+                 obj_scale: float, steps: int = 64, bound_radius: float = 0.07, start_depth: float = 0.2):
     """March z-depth along camera rays `dirs` (z = 1) against the GT SDF given in the object frame.
-    Returns (hit mask, z-depth)."""
+    `T_oc` is one (4,4) pose or a per-ray stack (n,4,4) -- all frames of a fruit are marched in ONE batch, so the
+    decoder is called `steps` times per fruit instead of `steps` x frames.  Returns (hit mask, z-depth)."""
     n = dirs.shape[0]
     dnorm = np.linalg.norm(dirs, axis=1)
-    A, t = T_oc[:3, :3], T_oc[:3, 3]
-    depth = np.full(n, 0.2, np.float64)
+    T_oc = np.asarray(T_oc)
+    depth = np.full(n, start_depth, np.float64)
     hit = np.zeros(n, bool)
     alive = np.ones(n, bool)
     for _ in range(steps):
-        p = (dirs * depth[:, None]) @ A.T + t
+        c = dirs * depth[:, None]
+        if T_oc.ndim == 2:
+            p = c @ T_oc[:3, :3].T + T_oc[:3, 3]
+        else:
+            p = np.einsum("nij,nj->ni", T_oc[:, :3, :3], c) + T_oc[:, :3, 3]
         r = np.linalg.norm(p, axis=1)
         s, _ = sdf_jac(latent, p.astype(np.float32))
-        s = np.where(r > 0.078, r - 0.07, s.astype(np.float64))
+        s = np.where(r > bound_radius + 0.008, r - bound_radius, s.astype(np.float64))
         newly = alive & (np.abs(s) < 2e-4)
         hit |= newly
         alive &= ~newly
-        alive &= depth < 0.7
+        alive &= depth < start_depth + 0.5
         step = 0.8 * s * obj_scale / dnorm
         depth = np.where(alive, depth + step, depth)
     return hit, depth.astype(np.float32)
@@ -107,7 +112,9 @@ def sphere_trace(sdf_jac: SdfJac, latent: np.ndarray, T_oc: np.ndarray, dirs: np
 
 def make_fruit(sdf_jac: SdfJac, latent_codes: np.ndarray, seed: int, index: int, n_pts: int = 2048,
                n_frames: int = 10, n_fg: int = 200, n_bg: int = 200, with_rays: bool = True,
-               leaf_fraction: float = 0.0, noise_m: float = 0.0, lattice: int = 48) -> SynthFruit:
+               leaf_fraction: float = 0.0, noise_m: float = 0.0, lattice: int = 48,
+               half_extent: float = 0.07, max_radius: float = 0.075) -> SynthFruit:
+    """`half_extent` / `max_radius` bound the object (defaults: sweet pepper, ~ +-5 cm; strawberry: 0.03 / 0.035)."""
     rng = np.random.default_rng(seed * 100003 + index)
     codes = np.asarray(latent_codes, np.float32)
     gt_latent = codes[(7919 * index) % codes.shape[0]].copy()
@@ -119,7 +126,7 @@ def make_fruit(sdf_jac: SdfJac, latent_codes: np.ndarray, seed: int, index: int,
     T_wo[:3, 3] = trans
     T_ow_gt = np.linalg.inv(T_wo)
 
-    pts_o = make_surface_points(sdf_jac, gt_latent, n_pts, rng)
+    pts_o = make_surface_points(sdf_jac, gt_latent, n_pts, rng, half_extent, max_radius)
     pts_w = pts_o.astype(np.float64) @ T_wo[:3, :3].T + T_wo[:3, 3]
     if noise_m > 0:
         pts_w = pts_w + rng.normal(0, noise_m, pts_w.shape)
@@ -131,12 +138,18 @@ def make_fruit(sdf_jac: SdfJac, latent_codes: np.ndarray, seed: int, index: int,
         u = np.linspace(-64, 64, lattice)
         uu, vv = np.meshgrid(u, u, indexing="xy")
         dirs = np.stack([uu.ravel() / fx, vv.ravel() / fx, np.ones(uu.size)], -1)
+        poses = []
         for k in range(n_frames):
             az = -0.6 + 1.2 * (k / max(n_frames - 1, 1))
             cam = np.array([0.4 * np.cos(az), 0.4 * np.sin(az), 0.05])
-            T_wc = _look_at(cam, np.zeros(3))
-            T_oc = T_ow_gt @ T_wc
-            hit, depth = sphere_trace(sdf_jac, gt_latent, T_oc, dirs, scale)
+            poses.append(_look_at(cam, np.zeros(3)))
+        # all frames marched in one batch (the per-ray results do not depend on the batching)
+        T_oc_all = np.repeat(np.stack([T_ow_gt @ T for T in poses]), dirs.shape[0], axis=0)
+        hit_all, depth_all = sphere_trace(sdf_jac, gt_latent, T_oc_all, np.tile(dirs, (n_frames, 1)), scale,
+                                          bound_radius=max_radius - 0.005)
+        for k in range(n_frames):
+            T_wc = poses[k]
+            hit, depth = hit_all[k * dirs.shape[0]:(k + 1) * dirs.shape[0]], depth_all[k * dirs.shape[0]:(k + 1) * dirs.shape[0]]
             fg_idx, bg_idx = np.nonzero(hit)[0], np.nonzero(~hit)[0]
             fg_sel = rng.choice(fg_idx, size=min(n_fg, fg_idx.size), replace=False) if fg_idx.size else fg_idx
             bg_sel = rng.choice(bg_idx, size=min(n_bg, bg_idx.size), replace=False) if bg_idx.size else bg_idx

@@ -50,7 +50,8 @@ extern "C" {
 #define HM_STATUS_MAX_ITER 0x08        /* optimizer.py:289                                  */
 #define HM_STATUS_FRAME_SKIPPED 0x10   /* optimizer.py:130-132 "This frame is not valid"    */
 #define HM_STATUS_SUBMAP_INVALID 0x20  /* optimizer.py:139-141 "This submap is not valid"   */
-#define HM_STATUS_F16_SATURATED 0x40   /* an activation hit the fp16 range of the TC engine */
+#define HM_STATUS_F16_SATURATED 0x40   /* a row of THIS fruit left the calibrated fp16 range of the TC engine */
+#define HM_STATUS_SOLVE_FAILED 0x80    /* singular / non-finite LM system: the fruit's state was left untouched  */
 
 typedef struct hm_context hm_context;
 
@@ -112,14 +113,24 @@ typedef struct hm_fruit_batch {
   int32_t* d_status;               /* [n_fruits] out  HM_STATUS_* bits                             */
 } hm_fruit_batch;
 
-/* Counters of the last optimise call (for roofline accounting). */
+/* Counters, cumulative since hm_create (for roofline accounting).  The row and tile counts are EXACT: the decoder
+ * kernels add the number of rows they actually evaluated (the device-side count of compacted ray samples / in-band samples, not
+ * the launch upper bound) to device counters that hm_get_counters reads back. */
 typedef struct hm_counters {
-  int64_t rows_forward;       /* decoder rows evaluated forward-only                         */
-  int64_t rows_jacobian;      /* decoder rows evaluated forward + input gradient             */
-  int64_t kernel_launches;    /* kernels of this library launched                            */
-  int64_t iterations;         /* LM iterations launched (max over fruits)                    */
-  int64_t decoder_launches;   /* decoder kernel launches timed while profiling was enabled   */
-  double decoder_ms;          /* sum of their CUDA-event durations (ms)                      */
+  int64_t rows_forward;       /* decoder rows evaluated forward-only                                            */
+  int64_t rows_jacobian;      /* decoder rows evaluated forward + input gradient                                */
+  int64_t kernel_launches;    /* kernels of this library launched                                               */
+  int64_t iterations;         /* LM iterations launched (max over fruits)                                       */
+  int64_t decoder_launches;   /* decoder kernel launches timed while profiling was enabled                      */
+  double decoder_ms;          /* sum of their CUDA-event durations (ms)                                         */
+  int64_t forward_launches;   /* ... of which forward-only launches                                             */
+  double forward_ms;
+  int64_t jacobian_launches;  /* ... and forward + input-gradient launches                                      */
+  double jacobian_ms;
+  int64_t tiles_forward;      /* 64-row tiles processed by forward-only / forward+gradient launches             */
+  int64_t tiles_jacobian;
+  int64_t tiles_dead_forward; /* ... of which took the exact zero-operand shortcut (all lin3 outputs of the      */
+  int64_t tiles_dead_jacobian;/*     tile pair are 0 after the ReLU)                              */
 } hm_counters;
 
 const char* hm_last_error(void);
@@ -130,10 +141,15 @@ int hm_create(hm_context** out, int device, const hm_decoder_desc* dec);
 void hm_destroy(hm_context* ctx);
 int hm_set_engine(hm_context* ctx, int engine);
 int hm_get_engine(const hm_context* ctx);
+/* Tensor-core engine: the zero-operand shortcut (on by default).  When every lin3 output of a 128-row tile pair is 0 after the
+ * ReLU -- true for every row of both shipped models -- the MMAs whose A operand is exactly zero are not issued.  The skipped
+ * products are exact zeros, so results are bit-identical with the shortcut off; the switch exists for that test and for
+ * measurements (hm_counters.tiles_dead_* count the tiles that took it). */
+int hm_set_zero_shortcut(hm_context* ctx, int on);
 /* Choose the power-of-two fp16 operand scales of the TC engine from sample rows [n][35] (device). */
 int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
-/* Counters are cumulative since hm_create.  With profiling enabled every decoder kernel launch is bracketed
- * by CUDA events on its stream; hm_get_counters then waits for the recorded events and adds their durations. */
+/* With profiling enabled every decoder kernel launch is bracketed by CUDA events on its stream; hm_get_counters synchronises the
+ * device, adds the recorded durations and reads the device-side row / tile counters. */
 int hm_get_counters(hm_context* ctx, hm_counters* out);
 /* Number of thread blocks of the tensor-core decoder, since the last call, in which an operand left the calibrated fp16 range
  * (the conversion saturates, the result is then NOT fp32-grade: re-run hm_calibrate on representative rows).  Synchronises the

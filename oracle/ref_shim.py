@@ -1,9 +1,10 @@
-"""Import shim that lets the UNMODIFIED reference (/root/reference) run on a CPU-only box.
+"""Import shim that lets the UNMODIFIED reference run on a CPU-only box (or on the CPU of a GPU box).
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py (run in the build container, where
-/root/reference is mounted) to produce the golden vectors under tests/golden/.  Nothing in the
-product path, the GPU tests, smoke() or bench.py imports this file: /root/reference does not
-exist on the GPU box.
+TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden*.py (run in the build container, where
+/root/reference is mounted) to produce the golden vectors under tests/golden/, and by
+oracle/ref_runner.py, which bench.py's baseline arms (`--impl reference`, `--impl reference-cuda`, the
+`cpu_baseline` leg) use to time the unmodified reference staged under baseline/_ref/
+(scripts/vendor_reference.py).  Nothing in the product path imports this file.
 
 What it neutralises:
   * wild_completion/utils.py:14-18 imports addict / plyfile / open3d / skimage at module top
@@ -18,7 +19,8 @@ import types
 REFERENCE_ROOT = "/root/reference"
 
 
-def install(reference_root: str = REFERENCE_ROOT):
+def install(reference_root: str = REFERENCE_ROOT, force_cpu: bool = False):
+    """force_cpu: neutralise the hard-coded `.cuda()` calls even when a GPU is present (the CPU baseline arm on the GPU box)."""
     import torch
 
     def _stub(name, **kw):
@@ -45,7 +47,7 @@ def install(reference_root: str = REFERENCE_ROOT):
         sk = _stub("skimage")
         sk.measure = _stub("skimage.measure")
 
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
         torch.cuda.synchronize = lambda *a, **k: None

@@ -40,12 +40,12 @@ def main():
     T0 = torch.from_numpy(np.tile(c["init_T_ow"], (n, 1, 1)).astype(np.float32)).cuda()
     ok = True
     for rd in (None, rds):
-        lat, T, it = optimize_sharded(opt, lat0, T0, pts, rd, cube_radius=float(c["cube_radius"]) if "cube_radius" in c else 0.08, pose_known=False)
+        lat, T, it, st = optimize_sharded(opt, lat0, T0, pts, rd, cube_radius=float(c["cube_radius"]) if "cube_radius" in c else 0.08, pose_known=False)
         if rd is None:
-            lr, Tr, ir, _ = opt.shape_opt_deepsdf_batch(lat0.clone(), T0.clone(), pts)
+            lr, Tr, ir, sr = opt.shape_opt_deepsdf_batch(lat0.clone(), T0.clone(), pts)
         else:
-            lr, Tr, ir, _ = opt.shape_pose_joint_opt_batch(lat0.clone(), T0.clone(), rds, pts, float(c["cube_radius"]) if "cube_radius" in c else 0.08, False)
-        same = torch.equal(lat, lr) and torch.equal(T, Tr.reshape(-1, 4, 4)) and torch.equal(it, ir.to(torch.int32))
+            lr, Tr, ir, sr = opt.shape_pose_joint_opt_batch(lat0.clone(), T0.clone(), rds, pts, float(c["cube_radius"]) if "cube_radius" in c else 0.08, False)
+        same = torch.equal(lat, lr) and torch.equal(T, Tr.reshape(-1, 4, 4)) and torch.equal(it, ir.to(torch.int32)) and torch.equal(st, sr.to(torch.int32))
         print(f"rank {dist.get_rank()}: {'joint' if rd is not None else 'shape'} sharded == single-rank: {same}  iters {it.tolist()}", flush=True)
         ok &= bool(same)
     dist.barrier()

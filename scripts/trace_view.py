@@ -1,4 +1,4 @@
-"""Print the decoder timeline captured by scratch/dbg_trace.py (gpurun_out/trace.npy): one unit of the first CTA pair."""
+"""Print the decoder timeline captured by scripts/probe_decoder.py trace (gpurun_out/trace.npy): one unit of the first CTA pair."""
 import sys
 import numpy as np
 tr = np.load(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/trace.npy')

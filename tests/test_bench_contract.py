@@ -24,9 +24,23 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "BLAS" in cb["sample"]
+    # the unmodified reference when it is staged (/root/reference here, baseline/_ref on the GPU box), else the numpy port
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert ("unmodified reference" in cb["sample"]) if cb["kind"] == "reference" else ("BLAS" in cb["sample"])
     assert d["e2e"] == {"value": d["value"], "unit": "fruits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 def test_reference_arm_other_ranks_print_nothing():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_reference_arm_falls_back_to_the_port_without_the_reference(monkeypatch):
+    """Without /root/reference and baseline/_ref the arm times the oracle port (torch BLAS, all cores) and says so."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import ref_runner
+    monkeypatch.setattr(ref_runner, "CANDIDATES", [])
+    res = bench.cpu_arm(bench.synth_io_cpu(), 2, 0, False)
+    assert res["kind"] == "port" and res["shape_iters"] == 2 and res["shape_s"] > 0 and "BLAS" in res["what"]
+    from oracle import hm_oracle as O
+    O.set_matmul(None)

@@ -55,7 +55,7 @@ class _StubOptimizer:
         for i, p in enumerate(pts):
             lat[i] += float(np.asarray(p).sum())
             T[i] = T[i] * 2.0
-        return lat, T, it, torch.zeros_like(it)
+        return lat, T, it, (it * 8 + 0x40 * (it % 2)).to(torch.int32)      # a recognisable status word per fruit
 
     def shape_pose_joint_opt_batch(self, lat, T, rds, pts, cr, pk):
         lat, T, it, st = self.shape_opt_deepsdf_batch(lat, T, pts)
@@ -73,14 +73,14 @@ def _driver_worker(rank, world, port, n_total, q):
     rds = [{"T_wc": [None] * (i % 3)} for i in range(n_total)]
     out = []
     for rd in (None, rds):
-        lat, T, it = optimize_sharded(_StubOptimizer(), lat0, T0, pts, rd, cube_radius=0.08, pose_known=np.arange(n_total) % 2 == 0)
-        out.append((lat.clone(), T.clone(), it.clone()))
+        lat, T, it, st = optimize_sharded(_StubOptimizer(), lat0, T0, pts, rd, cube_radius=0.08, pose_known=np.arange(n_total) % 2 == 0)
+        out.append((lat.clone(), T.clone(), it.clone(), st.clone()))
     dist.destroy_process_group()
     # single-process result of the same call
     ref = []
     for rd in (None, rds):
-        lat, T, it = optimize_sharded(_StubOptimizer(), lat0, T0, pts, rd, cube_radius=0.08, pose_known=np.arange(n_total) % 2 == 0)
-        ref.append((lat, T, it))
+        lat, T, it, st = optimize_sharded(_StubOptimizer(), lat0, T0, pts, rd, cube_radius=0.08, pose_known=np.arange(n_total) % 2 == 0)
+        ref.append((lat, T, it, st))
     ok = all(torch.equal(a, b) for o, r in zip(out, ref) for a, b in zip(o, r))
     q.put((rank, bool(ok)))
 

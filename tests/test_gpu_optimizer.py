@@ -258,3 +258,107 @@ def test_full_size_batch_properties():
     ref = lat0[f].astype(np.float64).copy()
     O.shape_opt_deepsdf(oracle_decoder(np.float64), cfg, ref, np.eye(4), pts[f])
     np.testing.assert_allclose(lat_b[f].cpu().numpy(), ref, rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("case_name,model", [("fruit_full", "sweetpepper_32"), ("fruit_berry", "strawberry_32")])
+def test_full_size_joint_step_replay_counts_membership_flips(case_name, model):
+    """Step replay at BASELINE.json's FULL joint sizes (fruit_full: 10 frames x 400 rays x 30 samples + 2048 points, wild_pepper.yaml)
+    and on the second shipped model (fruit_berry: strawberry_32, lab_berry.yaml).  Each iteration of the unmodified reference's run
+    is replayed as ONE device iteration from the reference's own state.  Sample membership is decided by hard thresholds
+    (in-sphere, |sdf| < th, de_do > 1e-6, occlusion): the goldens record how many decoder rows the reference selected per iteration
+    (forward hook), the device counts its rows exactly -- when the two agree no sample flipped and H, b must match to 1e-4
+    (north_star's tolerance); a flipped sample changes H, b by up to its own weight and is then counted, not hidden."""
+    from hortimapping_b200.decoder import Decoder
+    from hortimapping_b200.optimizer import Optimizer
+    c = load_npz(case_name)
+    cfg = zero_eps(cfg_of(c), 1)
+    cfg["device"] = "cuda"
+    if model == "sweetpepper_32":
+        opt, dec = make_opt(cfg)
+    else:
+        z = load_npz(model)
+        dec = Decoder([z[f"W{l}"] for l in range(9)], [z[f"b{l}"] for l in range(9)])
+        g = np.random.default_rng(0)
+        codes = z["latent_codes"]
+        cal = np.concatenate([codes[g.integers(0, codes.shape[0], 8192)], ((g.random((8192, 3)) * 2 - 1) * 0.075).astype(np.float32)], 1)
+        dec.calibrate(torch.from_numpy(cal))
+        opt = Optimizer(cfg, dec, None, None)
+    rd = render_data_of(c)
+    n = c["trace_H"].shape[0]
+    flips, worst_clean = 0, 0.0
+    for i in range(n):
+        lat0 = c["init_latent"] if i == 0 else c[f"after{i}_latent"]
+        T0 = c["init_T_ow"] if i == 0 else c[f"after{i}_T_ow"]
+        lat = torch.from_numpy(lat0.copy()).cuda().reshape(1, 32)
+        T = torch.from_numpy(T0.copy()).cuda().reshape(1, 4, 4)
+        c0 = dec.counters()
+        _, _, iters, status = opt.shape_pose_joint_opt_batch(lat, T, [rd], [c["points_w"]], float(c["cube_radius"]), bool(c["pose_known"]),
+                                                             iter_offset=i, max_iter=1)
+        c1 = dec.counters()
+        assert int(iters.item()) == 1 and not (int(status.item()) & 0x40)
+        H, b, dx = (t.cpu().numpy()[0] for t in opt.last_system(1))
+        d_fwd = c1["rows_forward"] - c0["rows_forward"] - int(c["trace_rows_fwd"][i])
+        d_jac = c1["rows_jacobian"] - c0["rows_jacobian"] - int(c["trace_rows_jac"][i])
+        eH, eb = rel(H, c["trace_H"][i]), rel(b, c["trace_b"][i])
+        if d_fwd == 0 and d_jac == 0:
+            worst_clean = max(worst_clean, eH, eb)
+            assert eH < 1e-4 and eb < 1e-4, (case_name, i, eH, eb)
+        else:
+            flips += abs(d_fwd) + abs(d_jac)
+            assert eH < 5e-3 and eb < 2e-2, (case_name, i, d_fwd, d_jac, eH, eb)
+        assert rel(lat.cpu().numpy()[0], c[f"after{i + 1}_latent"]) < 5e-2
+    assert flips <= 2 * n, (case_name, flips)
+    print(f"{case_name}: {n} iterations replayed, {flips} membership flips, worst H/b error without flips {worst_clean:.2e}")
+
+
+def test_lm_device_functions_vs_reference_vectors():
+    """exp_sim3 / exp_se3 (utils.py:220-324 incl. the theta <= eps, s == 0 and `c = 0 for s <= 0` branches) and the squared Huber
+    weights (utils.py:327-358 incl. the exact-zero residual) evaluated by the device functions of the LM step themselves, through
+    the test-only library's hooks, against vectors written by the unmodified reference (tests/golden/misc.npz)."""
+    import ctypes as C
+    from hortimapping_b200 import _lib, _testing
+    from tests.helpers import pepper_weights
+    W, b, _ = pepper_weights()
+    dec = _testing.testing_decoder(W, b)
+    L = _testing.lib()
+    m = load_npz("misc")
+    x = np.ascontiguousarray(m["exp_x"], np.float32)
+    n = x.shape[0]
+    for pd, key in ((7, "exp_sim3"), (6, "exp_se3")):
+        T = np.zeros((n, 16), np.float32)
+        _lib.check(L.hm_debug_exp_pose(dec.handle, x.ctypes.data_as(_lib.c_float_p), n, pd, T.ctypes.data_as(_lib.c_float_p)), "exp")
+        np.testing.assert_allclose(T.reshape(n, 4, 4), m[key], rtol=2e-6, atol=2e-7)
+    r = np.ascontiguousarray(m["huber_res"], np.float32)
+    w2 = np.zeros_like(r)
+    _lib.check(L.hm_debug_huber_w2(dec.handle, r.ctypes.data_as(_lib.c_float_p), r.size, 0.02, w2.ctypes.data_as(_lib.c_float_p)), "huber")
+    np.testing.assert_allclose(w2, m["huber_w2"].reshape(-1), rtol=2e-6, atol=0)
+    assert w2[5] == 0.0                                             # the exact-zero residual gets weight 0 (utils.py:337-338)
+
+
+def test_batched_api_rejects_bad_state_tensors():
+    """The C ABI takes raw device pointers: the batched API must refuse anything but contiguous float32 CUDA tensors of the
+    right shape on the decoder's GPU instead of corrupting memory."""
+    c = load_npz("fruit_wild")
+    opt, dec = make_opt(zero_eps(cfg_of(c), 1))
+    lat = torch.from_numpy(c["init_latent"].copy()).reshape(1, 32)
+    T = torch.from_numpy(c["init_T_ow"].copy()).reshape(1, 4, 4)
+    good = (lat.cuda(), T.cuda())
+    for bad_lat, bad_T in ((lat, T.cuda()), (lat.cuda().double(), T.cuda()), (lat.cuda().repeat(1, 2)[:, ::2], T.cuda()),
+                           (lat.cuda().reshape(32), T.cuda()), (lat.cuda(), T.cuda().reshape(16))):
+        with pytest.raises(ValueError):
+            opt.shape_opt_deepsdf_batch(bad_lat, bad_T, [c["points_w"]])
+    with pytest.raises(ValueError):
+        opt.shape_opt_deepsdf_batch(good[0], good[1], [c["points_w"], c["points_w"]])
+    opt.shape_opt_deepsdf_batch(good[0], good[1], [c["points_w"]])
+
+
+def test_degenerate_batches():
+    """A fruit without surface points stops with SUBMAP_INVALID and untouched state; its batch neighbours are unaffected."""
+    c = load_npz("fruit_wild")
+    opt, dec = make_opt(zero_eps(cfg_of(c), 2))
+    lat = torch.stack([torch.from_numpy(c["init_latent"].copy())] * 2).cuda()
+    T = torch.stack([torch.from_numpy(c["init_T_ow"].copy())] * 2).cuda()
+    _, _, iters, status = opt.shape_opt_deepsdf_batch(lat, T, [np.zeros((0, 3), np.float32), c["points_w"]])
+    assert iters.cpu().tolist() == [0, 2] and int(status[0].item()) & 0x20
+    np.testing.assert_array_equal(lat[0].cpu().numpy(), c["init_latent"])
+    assert not np.array_equal(lat[1].cpu().numpy(), c["init_latent"])
