@@ -100,7 +100,7 @@ def bind(L: C.CDLL) -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     L.hm_optimize_shape.argtypes = [C.c_void_p, C.POINTER(OptParams), C.POINTER(FruitBatch), C.c_void_p]
     L.hm_optimize_joint.argtypes = [C.c_void_p, C.POINTER(OptParams), C.POINTER(FruitBatch), C.c_void_p]
-    L.hm_get_last_system.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hm_get_last_system.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hm_optimize_shape_host.argtypes = [C.c_void_p, C.POINTER(OptParams), C.POINTER(FruitBatch)]
     L.hm_optimize_joint_host.argtypes = [C.c_void_p, C.POINTER(OptParams), C.POINTER(FruitBatch)]
     L.hm_isosurface.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -116,7 +116,8 @@ struct hm_context {
   float* d_last_b = nullptr;
   float* d_last_dx = nullptr;
   int last_est = 0;
-  int last_n_fruits = 0;
+  int last_n_fruits = 0;           // capacity of the three buffers above (fruits)
+  int last_call_fruits = 0;        // fruits of the most recent optimise call
 };
 
 int hm_ws_reserve(hm_context* ctx, size_t bytes);     // ctx->ws

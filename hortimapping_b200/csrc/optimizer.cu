@@ -936,6 +936,7 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
     ctx->last_n_fruits = nf;
   }
   ctx->last_est = est;
+  ctx->last_call_fruits = nf;
 
   // ---- upload the staged tables, build the O(rays) / O(points) tables on the device
   auto up = [&](void* d, const void* h, size_t bytes) -> cudaError_t { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
@@ -1029,9 +1030,11 @@ extern "C" int hm_optimize_joint(hm_context* ctx, const hm_opt_params* p, const 
   return hm_optimize_impl(ctx, p, batch, true, (cudaStream_t)stream);
 }
 
-extern "C" int hm_get_last_system(hm_context* ctx, float* d_H, float* d_b, float* d_dx, void* stream) {
+extern "C" int hm_get_last_system(hm_context* ctx, int32_t n_fruits, float* d_H, float* d_b, float* d_dx, void* stream) {
   HM_CHECK(ctx && ctx->d_last_H && ctx->last_est > 0, "hm_get_last_system: no optimisation has run");
-  const int est = ctx->last_est, nf = ctx->last_n_fruits;
+  HM_CHECK(n_fruits > 0 && n_fruits <= ctx->last_call_fruits, "hm_get_last_system: the last call optimised %d fruits, %d requested",
+           ctx->last_call_fruits, n_fruits);
+  const int est = ctx->last_est, nf = n_fruits;
   cudaStream_t st = (cudaStream_t)stream;
   if (d_H) HM_CUDA(cudaMemcpy2DAsync(d_H, sizeof(float) * est * est, ctx->d_last_H, sizeof(float) * kE * kE, sizeof(float) * est * est, nf, cudaMemcpyDeviceToDevice, st));
   if (d_b) HM_CUDA(cudaMemcpy2DAsync(d_b, sizeof(float) * est, ctx->d_last_b, sizeof(float) * kE, sizeof(float) * est, nf, cudaMemcpyDeviceToDevice, st));

@@ -145,7 +145,7 @@ class Optimizer(object):
         H = torch.empty(n_fruits, est, est, device=dec.device)
         b = torch.empty(n_fruits, est, device=dec.device)
         dx = torch.empty(n_fruits, est, device=dec.device)
-        check(dec._L.hm_get_last_system(dec.handle, H.data_ptr(), b.data_ptr(), dx.data_ptr(), _stream_ptr(dec.device)), "hm_get_last_system")
+        check(dec._L.hm_get_last_system(dec.handle, n_fruits, H.data_ptr(), b.data_ptr(), dx.data_ptr(), _stream_ptr(dec.device)), "hm_get_last_system")
         return H, b, dx
 
     def check_status(self, status: torch.Tensor) -> np.ndarray:

@@ -151,9 +151,10 @@ int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
 /* With profiling enabled every decoder kernel launch is bracketed by CUDA events on its stream; hm_get_counters synchronises the
  * device, adds the recorded durations and reads the device-side row / tile counters. */
 int hm_get_counters(hm_context* ctx, hm_counters* out);
-/* Number of thread blocks of the tensor-core decoder, since the last call, in which an operand left the calibrated fp16 range
- * (the conversion saturates, the result is then NOT fp32-grade: re-run hm_calibrate on representative rows).  Synchronises the
- * device and resets the count.  The optimisers report the same condition per call as HM_STATUS_F16_SATURATED. */
+/* Number of saturation events of the tensor-core decoder since the last call (one per 64-row tile and thread that saw an operand
+ * leave the calibrated fp16 range: the conversion saturates, the result is then NOT fp32-grade -- re-run hm_calibrate on
+ * representative rows).  Counts decoder calls and optimiser launches alike; synchronises the device and resets the count.  The
+ * optimisers additionally report the condition per FRUIT as HM_STATUS_F16_SATURATED. */
 int hm_saturation_count(hm_context* ctx, int64_t* h_count);
 int hm_profile_enable(hm_context* ctx, int on);
 
@@ -220,9 +221,10 @@ int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const float* d_laten
 int hm_optimize_shape(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* batch, void* stream);
 /* wild_completion/optimizer.py:28-302 shape_pose_joint_opt for a batch of fruits. */
 int hm_optimize_joint(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* batch, void* stream);
-/* Test hook: H [n_fruits][est*est], b [n_fruits][est], dx [n_fruits][est] of the LAST iteration run
- * (est = pose_dim + 32; pose_dim = 0 for hm_optimize_shape).  Device pointers, may be NULL. */
-int hm_get_last_system(hm_context* ctx, float* d_H, float* d_b, float* d_dx, void* stream);
+/* Diagnostics / test hook: H [n_fruits][est*est], b [n_fruits][est], dx [n_fruits][est] of the LAST iteration run, for the first
+ * n_fruits fruits of the last optimise call (an error if it had fewer; est = pose_dim + 32, pose_dim = 0 for hm_optimize_shape).
+ * Device pointers, may be NULL. */
+int hm_get_last_system(hm_context* ctx, int32_t n_fruits, float* d_H, float* d_b, float* d_dx, void* stream);
 
 /* Same optimisers with every pointer of `batch` a HOST pointer: copies in, runs, copies the results
  * (latents, T_ow, iter_count, status) back and synchronises.  This is the call bench.py's e2e times. */

@@ -209,6 +209,7 @@ def test_fp16_saturation_is_reported_not_silent():
         warnings.simplefilter("always")
         opt._report(st.cpu().numpy())
     assert any("F16_SATURATED" in str(w.message) for w in wlist)
+    assert dec.saturation_count() > 0                                    # the optimiser's launches count too; reading resets
     # calibrated on rows that represent what is evaluated: clean again, and fp32-grade
     from tests.gpu_helpers import random_rows
     mid, mid_cal = random_rows(4096, seed=5), random_rows(4096, seed=6)
@@ -348,6 +349,7 @@ def test_fp16_saturation_is_attributed_per_fruit_and_underflow_is_bounded():
     _, _, _, st = opt.shape_opt_deepsdf_batch(lat, T, [ok_pts, bad_pts, ok_pts])
     sat = [bool(int(s) & _lib.STATUS["F16_SATURATED"]) for s in st.cpu().tolist()]
     assert sat == [False, True, False], sat
+    assert dec.saturation_count() > 0                                    # (reading resets the event counter)
     # underflow side
     from tests.gpu_helpers import random_rows
     cal = random_rows(4096, seed=6)
