@@ -58,7 +58,8 @@ _lib = None
 EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_zero_shortcut", "hm_calibrate",
            "hm_get_counters", "hm_saturation_count", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
-           "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays"]
+           "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays",
+           "hm_dbscan", "hm_cloud_bounds", "hm_crop_mean_offset"]
 
 
 def lib() -> C.CDLL:
@@ -112,6 +113,10 @@ def bind(L: C.CDLL) -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.hm_nn_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.hm_isosurface_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+    c_double_p = C.POINTER(C.c_double)
+    L.hm_dbscan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+    L.hm_cloud_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, c_double_p, c_double_p, C.c_void_p]
+    L.hm_crop_mean_offset.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int64), c_double_p, C.c_void_p]
     return L
 
 

@@ -12,6 +12,7 @@ from (test_wild_completion.py:15-21, run_shape_completion_challenge.py:14-22):
     deepsdf.deep_sdf.workspace.{config_decoder,load_latent_vectors} -> hortimapping_b200.decoder
     metrics_3d.chamfer_distance.ChamferDistance, metrics_3d.precision_recall.PrecisionRecall -> hortimapping_b200.metrics
     wild_completion.utils.get_render_data / get_rays (attributes of the reference's own module) -> hortimapping_b200.render_data
+    wild_completion.utils.clean_mesh / clean_pcd / get_pose_init (utils.py:389-459)             -> hortimapping_b200.preprocess
 """
 from __future__ import annotations
 
@@ -68,6 +69,9 @@ def install(reference_root: str | None = None) -> None:
         from . import render_data as _rd
         wu = importlib.import_module("wild_completion.utils")
         wu.get_render_data, wu.get_rays = _rd.get_render_data, _rd.get_rays
+        # ... and the point-cloud preparation of utils.py:389-459 (DBSCAN cleaning, pose initialisation) to the device versions
+        from . import preprocess as _pp
+        wu.clean_mesh, wu.clean_pcd, wu.get_pose_init = _pp.clean_mesh, _pp.clean_pcd, _pp.get_pose_init
     except Exception:
         pass      # the reference's utils needs open3d / skimage; without them the host scripts cannot run anyway
 

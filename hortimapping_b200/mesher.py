@@ -49,7 +49,9 @@ class MeshExtractor(object):
     faces leave the device), "skimage" = the reference's own host call, "auto" (default) = skimage when it is importable
     (the mesh is then exactly what the reference builds from the same grid), else the device extractor."""
 
-    def __init__(self, decoder: Decoder, code_len=64, voxels_dim=64, cube_radius=1.0, iso: str = "auto"):
+    def __init__(self, decoder: Decoder, code_len=64, voxels_dim=64, cube_radius=1.0, iso: str = None):
+        import os
+        iso = iso or os.environ.get("HM_MESHER_ISO", "auto")      # the host scripts construct it without `iso`: the environment decides
         self.decoder = decoder
         self.code_len = code_len
         self.voxels_dim = voxels_dim

@@ -202,6 +202,20 @@ int hm_gather_rays(hm_context* ctx, const int32_t* d_pix, const float* d_depth, 
 int hm_nn_distance(hm_context* ctx, const double* d_query, int64_t n_query, const double* d_target, int64_t n_target,
                    double* d_dist, void* stream);
 
+/* wild_completion/utils.py:408-419 clean_pcd, device side: DBSCAN labels of d_points [n][3] (fp64) exactly as open3d's
+ * PointCloud::cluster_dbscan(eps, min_points) assigns them (neighbourhood |p - q|^2 < eps^2 including p itself; clusters numbered
+ * by their smallest core index; border points take the smallest cluster number among their core neighbours; noise = -1), computed
+ * order-independently in parallel.  d_labels [n] int32; h_n_clusters may be NULL.  ctx may be NULL (current device).
+ * Synchronises the stream. */
+int hm_dbscan(hm_context* ctx, const double* d_points, int64_t n, double eps, int32_t min_points, int32_t* d_labels,
+              int32_t* h_n_clusters, void* stream);
+/* wild_completion/utils.py:426-427 (get_axis_aligned_bounding_box): component-wise min / max of d_points [n][3] (fp64). */
+int hm_cloud_bounds(hm_context* ctx, const double* d_points, int64_t n, double* h_min3, double* h_max3, void* stream);
+/* wild_completion/utils.py:447-455: the points of d_points inside the box [h_box_min3, h_box_max3] (inclusive, open3d's
+ * AxisAlignedBoundingBox crop): their count and the mean of (p - h_center3). */
+int hm_crop_mean_offset(hm_context* ctx, const double* d_points, int64_t n, const double* h_box_min3, const double* h_box_max3,
+                        const double* h_center3, int64_t* h_count, double* h_mean3, void* stream);
+
 /* wild_completion/loss.py:219-243 compute_sdf_loss: res[n], J_pose[n][pose_dim], J_code[n][32]. */
 int hm_sdf_loss(hm_context* ctx, const float* d_latent, const float* d_pts_obj, int64_t n, int32_t scale_on,
                 float* d_res, float* d_J_pose, float* d_J_code, void* stream);
