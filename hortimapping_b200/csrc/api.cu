@@ -129,6 +129,7 @@ extern "C" void hm_destroy(hm_context* ctx) {
   if (ctx->io_arena) cudaFree(ctx->io_arena);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
+  if (ctx->busy_event) cudaEventDestroy(ctx->busy_event);
   if (ctx->mesh_ws) cudaFree(ctx->mesh_ws);
   if (ctx->mesh_out) cudaFree(ctx->mesh_out);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
@@ -206,6 +207,7 @@ extern "C" int hm_profile_enable(hm_context* ctx, int on) {
 
 extern "C" int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream) {
   HM_CHECK(ctx && d_rows && n > 0, "hm_calibrate: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   hm_rows rows = {d_rows, nullptr, nullptr, nullptr, n, nullptr};
   float absmax[16];
@@ -244,6 +246,7 @@ int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, 
 
 extern "C" int hm_sdf_forward(hm_context* ctx, const float* d_latent, const float* d_xyz, int64_t n, float* d_sdf, void* stream) {
   HM_CHECK(ctx && d_latent && (n == 0 || (d_xyz && d_sdf)) && n >= 0, "hm_sdf_forward: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   hm_rows rows = {nullptr, d_xyz, d_latent, nullptr, n, nullptr};
   return hm_decode(ctx, rows, d_sdf, nullptr, (cudaStream_t)stream);
@@ -251,6 +254,7 @@ extern "C" int hm_sdf_forward(hm_context* ctx, const float* d_latent, const floa
 
 extern "C" int hm_sdf_forward_rows(hm_context* ctx, const float* d_rows, int64_t n, float* d_sdf, void* stream) {
   HM_CHECK(ctx && (n == 0 || (d_rows && d_sdf)) && n >= 0, "hm_sdf_forward_rows: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   hm_rows rows = {d_rows, nullptr, nullptr, nullptr, n, nullptr};
   return hm_decode(ctx, rows, d_sdf, nullptr, (cudaStream_t)stream);
@@ -259,6 +263,7 @@ extern "C" int hm_sdf_forward_rows(hm_context* ctx, const float* d_rows, int64_t
 extern "C" int hm_sdf_jacobian(hm_context* ctx, const float* d_latent, const float* d_xyz, int64_t n, float* d_sdf,
                                float* d_jac, void* stream) {
   HM_CHECK(ctx && d_latent && (n == 0 || (d_xyz && d_sdf && d_jac)) && n >= 0, "hm_sdf_jacobian: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   hm_rows rows = {nullptr, d_xyz, d_latent, nullptr, n, nullptr};
   return hm_decode(ctx, rows, d_sdf, d_jac, (cudaStream_t)stream);
@@ -266,6 +271,7 @@ extern "C" int hm_sdf_jacobian(hm_context* ctx, const float* d_latent, const flo
 
 extern "C" int hm_sdf_jacobian_rows(hm_context* ctx, const float* d_rows, int64_t n, float* d_sdf, float* d_jac, void* stream) {
   HM_CHECK(ctx && (n == 0 || (d_rows && d_sdf && d_jac)) && n >= 0, "hm_sdf_jacobian_rows: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   hm_rows rows = {d_rows, nullptr, nullptr, nullptr, n, nullptr};
   return hm_decode(ctx, rows, d_sdf, d_jac, (cudaStream_t)stream);
@@ -296,6 +302,7 @@ extern "C" int hm_voxel_grid(hm_context* ctx, int32_t vol_dim, float cube_radius
 
 extern "C" int hm_sdf_grid(hm_context* ctx, const float* d_latent, int32_t vol_dim, float cube_radius, float* d_sdf, void* stream) {
   HM_CHECK(ctx && d_latent && d_sdf && vol_dim >= 2 && vol_dim <= 1024, "hm_sdf_grid: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   int64_t total = (int64_t)vol_dim * vol_dim * vol_dim;
   hm_rows rows = {nullptr, nullptr, d_latent, nullptr, total, nullptr};

@@ -118,6 +118,28 @@ struct hm_context {
   int last_est = 0;
   int last_n_fruits = 0;           // capacity of the three buffers above (fruits)
   int last_call_fruits = 0;        // fruits of the most recent optimise call
+  // cross-stream ordering of the calls of this context (hm_stream_scope)
+  cudaEvent_t busy_event = nullptr;
+  cudaStream_t last_stream = nullptr;
+};
+
+// A context owns scratch that every call reuses (decoder workspaces, per-CTA ReLU masks, device counters, the optimiser workspace,
+// the last-system buffers), so two calls of the SAME context must not overlap on the GPU even when they are issued on different
+// streams.  Every public entry point that touches that scratch opens one of these: if the previous call ran on another stream, the
+// new stream first waits (on the GPU, no host synchronisation) for the event recorded when that call was enqueued; on exit the
+// event is re-recorded on the current stream.  Calls from different host THREADS still need external locking (header).
+struct hm_stream_scope {
+  hm_context* ctx;
+  cudaStream_t st;
+  hm_stream_scope(hm_context* c, cudaStream_t s) : ctx(c), st(s) {
+    if (ctx && ctx->busy_event && ctx->last_stream != st) cudaStreamWaitEvent(st, ctx->busy_event, 0);
+  }
+  ~hm_stream_scope() {
+    if (!ctx) return;
+    if (!ctx->busy_event && cudaEventCreateWithFlags(&ctx->busy_event, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(ctx->busy_event, st);
+    ctx->last_stream = st;
+  }
 };
 
 int hm_ws_reserve(hm_context* ctx, size_t bytes);     // ctx->ws

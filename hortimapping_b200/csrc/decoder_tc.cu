@@ -809,6 +809,7 @@ int hm_tc_init(hm_context* ctx) {
     }
   }
   const int copies = hm_tc_blob_copies();
+  if (ctx->d_tc_blob) HM_CUDA(cudaDeviceSynchronize());      // re-calibration: no kernel on any stream may still read the old blob / biases
   if (ctx->d_tc_blob && (ctx->tc_blob_bytes != blob.size() || ctx->tc_blob_copies != copies)) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
   if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size() * copies));
   ctx->tc_blob_bytes = blob.size();

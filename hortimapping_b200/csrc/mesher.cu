@@ -166,6 +166,7 @@ __global__ void vertex_affine_kernel(int64_t n3, double cube_radius, float* __re
 extern "C" int hm_isosurface(hm_context* ctx, const float* d_sdf, int32_t n, double level, double spacing, int64_t* h_n_verts,
                              int64_t* h_n_faces, void* stream) {
   HM_CHECK(ctx && d_sdf && h_n_verts && h_n_faces && n >= 2 && n <= 640, "hm_isosurface: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_pts = (int64_t)n * n * n, n_edges = n_pts * 7, n_cells = (int64_t)(n - 1) * (n - 1) * (n - 1);
@@ -227,6 +228,7 @@ extern "C" int hm_isosurface(hm_context* ctx, const float* d_sdf, int32_t n, dou
 // apply_affine != 0 the vertices become (v - 1) * cube_radius (wild_completion/utils.py:583-585).
 extern "C" int hm_isosurface_fetch(hm_context* ctx, float* d_verts, int32_t* d_faces, int32_t apply_affine, double cube_radius, void* stream) {
   HM_CHECK(ctx && ctx->mesh_out, "hm_isosurface_fetch: no mesh (call hm_isosurface first)");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };

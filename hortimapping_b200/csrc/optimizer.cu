@@ -409,60 +409,90 @@ __global__ void point_jacobian_kernel(int64_t n_points, int pose_dim, const floa
   for (int c = 0; c < est; ++c) J[i * kE + c] = j[c];
 }
 
-// optimizer.py:152-159,189-190: partial sums of w * J^T J (upper triangle) and w * J^T r over <= 128 items
+// optimizer.py:152-159,189-190: partial sums of w * J^T J (upper triangle) and w * J^T r over <= 128 items (one block).
+// The block's Jacobian rows are staged in shared memory with coalesced loads ([J | r] per item, rows padded to 44 floats), then
+// each thread accumulates one 4 x 4 tile of J^T W [J | r] over the items in item order (two 16-byte shared loads and 16 FMAs per
+// item).  Tiles below the diagonal are computed too (the arithmetic is trivial) but not written.  Every output is the same
+// left-to-right fmaf chain over the items as a scalar loop, so partials are deterministic and independent of the tiling.
+constexpr int kJRow = 44;       // kE + 1 (the residual column) rounded up to a multiple of 4
+
 __global__ void __launch_bounds__(128) normal_eq_kernel(const RedBlock* __restrict__ blocks, int est, int iter, DevParams P,
                                                         const float* __restrict__ J_d, const float* __restrict__ J_m,
                                                         const float* __restrict__ res_d, const float* __restrict__ res_m,
                                                         const int32_t* __restrict__ ray_k, const float* __restrict__ J_r,
                                                         const float* __restrict__ res_r, int r_stride, const uint8_t* __restrict__ active,
                                                         float* __restrict__ partials, int32_t* __restrict__ block_items) {
-  __shared__ float sJ[kRedItems][kE + 1];
-  __shared__ float sW[kRedItems], sR[kRedItems];
+  __shared__ __align__(16) float sJ[kRedItems][kJRow];
+  __shared__ float sW[kRedItems];
   __shared__ int s_cnt;
   const RedBlock B = blocks[blockIdx.x];
   float* out = partials + (size_t)blockIdx.x * kPartial;
   if (!active[B.fruit]) return;
   if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
   const float* J = (B.term == 0) ? J_d : (B.term == 1) ? J_m : J_r;
   const float* R = (B.term == 0) ? res_d : (B.term == 1) ? res_m : res_r;
+  const int stride = (B.term == 2) ? r_stride : kE;      // the latent-only loop reads the decoder's Jacobian rows in place
   const bool robust = iter >= P.robust_iter;
+  const int t = threadIdx.x;
+  for (int e = t; e < kRedItems * kJRow; e += 128) (&sJ[0][0])[e] = 0.f;
+  __syncthreads();
+  // coalesced copy of the block's rows: element e of the contiguous range [start * stride, (start + count) * stride)
+  const float* src = J + (size_t)B.start * stride;
+  for (int e = t; e < B.count * stride; e += 128) {
+    const int row = e / stride, col = e - row * stride;
+    if (col < est) sJ[row][col] = src[e];
+  }
+  __syncthreads();
   {
-    const int t = threadIdx.x;
-    float w = 0.f, rr = 0.f;
+    float w = 0.f;
     if (t < B.count) {
       const int64_t it = B.start + t;
       const bool ok = (B.term == 2) ? true : (ray_k[it] > 0);
       if (ok) {
-        rr = R[it];
+        const float rr = R[it];
         w = 1.f;
         if (robust && B.term == 0) w = huber_w2(rr, P.t_depth);      // optimizer.py:145-149
         if (robust && B.term == 2) w = huber_w2(rr, P.t_recon);      // :183-187
+        sJ[t][est] = rr;
         atomicAdd(&s_cnt, 1);
+      } else {
+        for (int c = 0; c < est; ++c) sJ[t][c] = 0.f;                 // a ray without surviving samples contributes nothing
       }
-      const int stride = (B.term == 2) ? r_stride : kE;      // the latent-only loop reads the decoder's Jacobian rows in place
-      for (int c = 0; c < est; ++c) sJ[t][c] = ok ? J[it * stride + c] : 0.f;
-    } else {
-      for (int c = 0; c < est; ++c) sJ[t][c] = 0.f;
     }
     sW[t] = w;
-    sR[t] = rr;
   }
   __syncthreads();
-  const int tri = est * (est + 1) / 2;
-  for (int e = threadIdx.x; e < tri + est; e += 128) {
-    float acc = 0.f;
-    if (e < tri) {
-      // unrank the upper-triangle index e -> (a, b), a <= b
-      int a = 0, rem = e;
-      while (rem >= est - a) { rem -= est - a; ++a; }
-      const int b = a + rem;
-      for (int i = 0; i < kRedItems; ++i) acc = fmaf(sW[i] * sJ[i][a], sJ[i][b], acc);
-    } else {
-      const int a = e - tri;
-      for (int i = 0; i < kRedItems; ++i) acc = fmaf(sW[i] * sJ[i][a], sR[i], acc);
+  const int na = (est + 3) / 4, nb = (est + 4) / 4;      // 4-wide blocks of the rows a (0 .. est-1) and columns b (0 .. est, column est = r)
+  if (t < na * nb) {
+    const int ta = t / nb, tb = t - ta * nb;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    if (tb >= ta) {                                        // tiles entirely below the diagonal are never written
+      for (int i = 0; i < kRedItems; ++i) {
+        const float4 ja = *reinterpret_cast<const float4*>(&sJ[i][4 * ta]);
+        const float4 jb = *reinterpret_cast<const float4*>(&sJ[i][4 * tb]);
+        const float w = sW[i];
+        const float wa[4] = {w * ja.x, w * ja.y, w * ja.z, w * ja.w};
+        const float bb[4] = {jb.x, jb.y, jb.z, jb.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(wa[x], bb[y], acc[x][y]);
+      }
+      const int tri = est * (est + 1) / 2;
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int ra = 4 * ta + x, cb = 4 * tb + y;
+          if (ra >= est || cb > est) continue;
+          if (cb == est) out[tri + ra] = acc[x][y];                                         // J^T W r
+          else if (cb >= ra) out[ra * est - ra * (ra - 1) / 2 + (cb - ra)] = acc[x][y];      // upper triangle, row-major
+        }
     }
-    out[e] = acc;
   }
   if (threadIdx.x == 0) block_items[blockIdx.x] = s_cnt;
 }
@@ -645,65 +675,108 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(SolveArgs a, DevPa
     for (int e = tid; e < est * est; e += kSolveThreads) a.last_H[(size_t)f * kE * kE + e] = (float)sH[e / est][e % est];
     if (tid < est) a.last_b[(size_t)f * kE + tid] = (float)sH[tid][est];
   }
-  double bmax = 0.0;
-  if (tid == 0)
-    for (int i = 0; i < est; ++i) bmax = fmax(bmax, fabs((double)(float)sH[i][est]));
-  __syncthreads();
-  // delta_x = H^-1 b (:234): Gauss-Jordan elimination with partial pivoting on [H | b] in fp64, one element per thread.  Step k
-  // reads row k and column k and writes neither (column k of the other rows is simply never read again), so one barrier
-  // separates the steps.
-  for (int k = 0; k < est; ++k) {
-    if (tid < 32) {
-      // arg max_i |H[i][k]|, i >= k, the FIRST maximum on ties: lanes cover rows k + lane and k + lane + 32 (est <= 39)
-      double best = -1.0;
-      int p = est;
-      for (int i = k + tid; i < est; i += 32) {
-        const double v = fabs(sH[i][k]);
-        if (v > best) { best = v; p = i; }
-      }
+  // max |b| for the gradient stop test (:276), by warp 0
+  __shared__ float s_bmax, s_cmax;
+  __shared__ int s_cnan, s_st_pose;
+  __shared__ float s_dx[kE];
+  if (tid < 32) {
+    float m = 0.f;
+    for (int i = tid; i < est; i += 32) m = fmaxf(m, fabsf((float)sH[i][est]));
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const int op = __shfl_xor_sync(0xffffffffu, p, off);
-        if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
-      }
-      if (tid == 0) {
-        s_piv = p;
-        if (!(best > 0.0) || !isfinite(best)) s_fail = 1;          // singular or non-finite system
-      }
-    }
-    __syncthreads();
-    if (s_fail) break;
-    const int p = s_piv;
-    if (p != k && ty == 0)
-      for (int c = tx; c <= est; c += 32) { const double t = sH[k][c]; sH[k][c] = sH[p][c]; sH[p][c] = t; }
-    __syncthreads();
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (tid == 0) s_bmax = m;
+  }
+  // delta_x = H^-1 b (:234) by Gauss-Jordan elimination on [H | b] in fp64, one matrix element per thread.  H is symmetric
+  // positive definite here (J^T W J with non-negative weights + code regulariser + LM damping), for which elimination without
+  // row exchanges is backward stable; so the fast path takes the diagonal as pivot: step k reads row k and column k and writes
+  // neither (column k of the other rows is simply never read again), ONE barrier per step.  A pivot that is not a positive finite
+  // number (a semi-definite system, e.g. Gauss-Newton with an unobservable pose) sends the fruit to the partial-pivoting path on a
+  // saved copy of the system -- what torch.inverse's LU does.
+  __shared__ double sH0[kE][kE + 2];
+  for (int e = tid; e < est * (est + 1); e += kSolveThreads) sH0[e / (est + 1)][e % (est + 1)] = sH[e / (est + 1)][e % (est + 1)];
+  __syncthreads();
+  for (int k = 0; k < est; ++k) {
     const double piv = sH[k][k];
+    if (!(piv > 0.0) || !isfinite(piv)) { if (tid == 0) s_fail = 1; }
+    const double rp = 1.0 / piv;
     for (int i = ty; i < est; i += 32) {
       if (i == k) continue;
-      const double m = sH[i][k] / piv;
+      const double m = sH[i][k] * rp;
       for (int c = tx; c <= est; c += 32)
         if (c > k) sH[i][c] -= m * sH[k][c];
     }
     __syncthreads();
+    if (s_fail) break;
   }
-  if (tid == 0) {
-    float dx[kE];
-    bool bad = s_fail != 0;
-    for (int i = 0; i < est && !bad; ++i) {
-      dx[i] = (float)(sH[i][est] / sH[i][i]);
-      if (!isfinite(dx[i])) bad = true;
+  if (s_fail) {
+    // ---- partial pivoting (first maximum on ties), three barriers per step
+    __syncthreads();
+    for (int e = tid; e < est * (est + 1); e += kSolveThreads) sH[e / (est + 1)][e % (est + 1)] = sH0[e / (est + 1)][e % (est + 1)];
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    for (int k = 0; k < est; ++k) {
+      if (tid < 32) {
+        double best = -1.0;
+        int p = est;
+        for (int i = k + tid; i < est; i += 32) {
+          const double v = fabs(sH[i][k]);
+          if (v > best) { best = v; p = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+          const int op = __shfl_xor_sync(0xffffffffu, p, off);
+          if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        if (tid == 0) {
+          s_piv = p;
+          if (!(best > 0.0) || !isfinite(best)) s_fail = 1;          // singular or non-finite system
+        }
+      }
+      __syncthreads();
+      if (s_fail) break;
+      const int p = s_piv;
+      if (p != k && ty == 0)
+        for (int c = tx; c <= est; c += 32) { const double t = sH[k][c]; sH[k][c] = sH[p][c]; sH[p][c] = t; }
+      __syncthreads();
+      const double piv = sH[k][k];
+      for (int i = ty; i < est; i += 32) {
+        if (i == k) continue;
+        const double m = sH[i][k] / piv;
+        for (int c = tx; c <= est; c += 32)
+          if (c > k) sH[i][c] -= m * sH[k][c];
+      }
+      __syncthreads();
     }
-    if (bad) {
-      // torch.inverse raises on a singular matrix; here the fruit stops with its state untouched and a status bit
-      atomicOr(&a.status[f], HM_STATUS_SOLVE_FAILED);
-      a.active[f] = 0;
-      return;
-    }
-    if (a.last_dx) for (int i = 0; i < est; ++i) a.last_dx[(size_t)f * kE + i] = dx[i];
-    int st = 0;
-    float delta_tran = 0.f, delta_rot = 0.f, delta_scale = 0.f;
+  }
+  if (tid < est) {
+    const float d = s_fail ? 0.f : (float)(sH[tid][est] / sH[tid][tid]);
+    if (!isfinite(d)) s_fail = 1;
+    s_dx[tid] = d;
+  }
+  __syncthreads();
+  if (s_fail) {
+    // torch.inverse raises on a singular matrix; here the fruit stops with its state untouched and a status bit
+    if (tid == 0) { atomicOr(&a.status[f], HM_STATUS_SOLVE_FAILED); a.active[f] = 0; }
+    return;
+  }
+  if (a.last_dx && tid < est) a.last_dx[(size_t)f * kE + tid] = s_dx[tid];
+  // ---- update (:235-253) and stop tests (:276-291): the latent by warp 0, the pose by one lane of warp 1, concurrently
+  if (tid < 32) {
+    const float dc = s_dx[pd + tid];
+    const float ln = lat[tid] + dc;                                        // :248 / :401
+    lat[tid] = ln;
+    const float q = fabsf(dc / (ln + 1e-12f));                             // :280 uses the updated latent
+    const unsigned nan_any = __ballot_sync(0xffffffffu, q != q);
+    float m = (q != q) ? 0.f : q;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (tid == 0) { s_cmax = m; s_cnan = nan_any != 0u; }
+  } else if (tid == 32) {
+    int pose_conv = 0;
     if (a.joint) {
+      float dx[kE];
+      for (int i = 0; i < pd; ++i) dx[i] = s_dx[i];
       if (a.pose_known[f]) for (int i = 0; i < 6; ++i) dx[i] = 0.f;        // :237-238 (scale is still optimised)
       float dT[16], Tn[16];
       exp_pose(dx, pd, dT);                                                // :242-245
@@ -716,26 +789,22 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(SolveArgs a, DevPa
         }
       for (int i = 0; i < 16; ++i) T[i] = Tn[i];                           // :247
       const float cur_scale = powf(det3(Tn), (float)(-1.0 / 3.0));         // :250
-      delta_scale = powf(det3(dT), (float)(1.0 / 3.0));                    // :251
-      delta_tran = sqrtf(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]) * cur_scale;   // :252
+      const float delta_scale = powf(det3(dT), (float)(1.0 / 3.0));        // :251
+      const float delta_tran = sqrtf(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]) * cur_scale;   // :252
       const float trace = (dT[0] + dT[5] + dT[10]) * cur_scale;
-      delta_rot = fabsf(acosf((trace - 1.f) / 2.f)) * (float)(180.0 / 3.14159265358979323846);   // :253 (NaN when |arg| > 1)
+      const float delta_rot = fabsf(acosf((trace - 1.f) / 2.f)) * (float)(180.0 / 3.14159265358979323846);   // :253 (NaN when |arg| > 1)
+      pose_conv = !a.pose_known[f] && delta_tran < (float)P.eps_t && delta_rot < (float)P.eps_r && delta_scale < (float)P.eps_s;   // :285
     }
-    float cmax = 0.f;
-    bool cnan = false;
-    for (int c = 0; c < HM_LATENT; ++c) {
-      const float dc = dx[pd + c];
-      lat[c] += dc;                                                        // :248 / :401
-      const float q = fabsf(dc / (lat[c] + 1e-12f));                       // :280 uses the updated latent
-      if (q != q) cnan = true;
-      cmax = fmaxf(cmax, q);
-    }
+    s_st_pose = pose_conv;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int st = 0;
     a.iter_count[f] = a.iter + 1 - a.iter_first;
     const bool guard = a.iter > 1;
-    if ((float)bmax < (float)P.eps_g && guard) st |= HM_STATUS_CONV_GRADIENT;                    // :276
-    else if (!cnan && cmax < (float)P.eps_c && guard) st |= HM_STATUS_CONV_CODE;                 // :280
-    else if (a.joint && !a.pose_known[f] && delta_tran < (float)P.eps_t && delta_rot < (float)P.eps_r &&
-             delta_scale < (float)P.eps_s && guard) st |= HM_STATUS_CONV_POSE;                   // :285
+    if (s_bmax < (float)P.eps_g && guard) st |= HM_STATUS_CONV_GRADIENT;                         // :276
+    else if (!s_cnan && s_cmax < (float)P.eps_c && guard) st |= HM_STATUS_CONV_CODE;             // :280
+    else if (a.joint && s_st_pose && guard) st |= HM_STATUS_CONV_POSE;                           // :285
     if (!st && a.iter == a.iter_last) st |= HM_STATUS_MAX_ITER;                                  // :289
     if (st) { atomicOr(&a.status[f], st); a.active[f] = 0; }
   }
@@ -1024,14 +1093,19 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
 }
 
 extern "C" int hm_optimize_shape(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* batch, void* stream) {
+  HM_CHECK(ctx, "hm_optimize_shape: null context");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   return hm_optimize_impl(ctx, p, batch, false, (cudaStream_t)stream);
 }
 extern "C" int hm_optimize_joint(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* batch, void* stream) {
+  HM_CHECK(ctx, "hm_optimize_joint: null context");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   return hm_optimize_impl(ctx, p, batch, true, (cudaStream_t)stream);
 }
 
 extern "C" int hm_get_last_system(hm_context* ctx, int32_t n_fruits, float* d_H, float* d_b, float* d_dx, void* stream) {
   HM_CHECK(ctx && ctx->d_last_H && ctx->last_est > 0, "hm_get_last_system: no optimisation has run");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CHECK(n_fruits > 0 && n_fruits <= ctx->last_call_fruits, "hm_get_last_system: the last call optimised %d fruits, %d requested",
            ctx->last_call_fruits, n_fruits);
   const int est = ctx->last_est, nf = n_fruits;
@@ -1045,6 +1119,7 @@ extern "C" int hm_get_last_system(hm_context* ctx, int32_t n_fruits, float* d_H,
 // host-buffer variant: the call bench.py times end to end (H2D of every input, D2H of the results)
 static int optimize_host(hm_context* ctx, const hm_opt_params* p, const hm_fruit_batch* hb, bool joint) {
   HM_CHECK(ctx && p && hb && hb->n_fruits > 0, "hm_optimize_*_host: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)0);
   HM_CUDA(cudaSetDevice(ctx->device));
   const int nf = hb->n_fruits;
   const int64_t n_points = hb->h_point_offsets[nf];
@@ -1102,6 +1177,7 @@ extern "C" int hm_optimize_joint_host(hm_context* ctx, const hm_opt_params* p, c
 extern "C" int hm_sdf_loss(hm_context* ctx, const float* d_latent, const float* d_pts_obj, int64_t n, int32_t scale_on,
                            float* d_res, float* d_J_pose, float* d_J_code, void* stream) {
   HM_CHECK(ctx && d_latent && d_pts_obj && d_res && d_J_pose && d_J_code && n > 0, "hm_sdf_loss: bad argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   HM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int pose_dim = scale_on ? 7 : 6;
@@ -1130,6 +1206,7 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
                               float* d_J_m, int32_t* h_n_valid_samples, void* stream) {
   HM_CHECK(ctx && p && d_latent && d_rays && d_depth_obs && h_T_oc && h_depths && d_ray_valid && d_res_d && d_J_d && d_res_m && d_J_m,
            "hm_render_loss: null argument");
+  hm_stream_scope scope_(ctx, (cudaStream_t)stream);
   const int M = p->n_depth_samples;
   HM_CHECK(n_rays > 0 && n_fg >= 0 && n_fg <= n_rays && M >= 2 && M <= kMaxM, "hm_render_loss: bad sizes");
   HM_CUDA(cudaSetDevice(ctx->device));

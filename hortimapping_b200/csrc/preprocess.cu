@@ -182,7 +182,7 @@ int use_device(hm_context* ctx) {
 
 extern "C" int hm_dbscan(hm_context* ctx, const double* d_points, int64_t n, double eps, int32_t min_points, int32_t* d_labels,
                          int32_t* h_n_clusters, void* stream) {
-  HM_CHECK(d_points && d_labels && n >= 0 && n < (int64_t)1 << 24 && eps >= 0, "hm_dbscan: bad argument");
+  HM_CHECK(n >= 0 && n < ((int64_t)1 << 24) && eps >= 0 && (n == 0 || (d_points && d_labels)), "hm_dbscan: bad argument");
   if (h_n_clusters) *h_n_clusters = 0;
   if (n == 0) return HM_OK;
   int rc = use_device(ctx);

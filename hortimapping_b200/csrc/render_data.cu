@@ -54,7 +54,7 @@ __global__ void id_bbox_init_kernel(int n_ids, int32_t* __restrict__ table) {
 // Ordered compaction of the crop grid (rows hh[], columns ww[], row-major as utils.py:66-71): background candidates are the
 // grid pixels whose id differs from the fruit's (:72), foreground those with the id AND a valid depth (:81).  One block walks
 // the grid in chunks of blockDim.x and keeps running offsets, so the output order is the reference's.
-__global__ void __launch_bounds__(1024) crop_candidates_kernel(const int32_t* __restrict__ id_img, const float* __restrict__ depth, int w,
+__global__ void __launch_bounds__(1024) crop_candidates_kernel(const int32_t* __restrict__ id_img, const float* __restrict__ depth, int h, int w,
                                                                int32_t submap_id, const int32_t* __restrict__ hh, int crop_h,
                                                                const int32_t* __restrict__ ww, int crop_w, int32_t* __restrict__ pix_bg,
                                                                float* __restrict__ depth_bg, int32_t* __restrict__ pix_fg,
@@ -72,10 +72,12 @@ __global__ void __launch_bounds__(1024) crop_candidates_kernel(const int32_t* __
     if (i < total) {
       v = hh[i / crop_w];
       u = ww[i % crop_w];
-      const int32_t id = id_img[(int64_t)v * w + u];
-      d = depth[(int64_t)v * w + u];
-      is_bg = (id != submap_id);
-      is_fg = (id == submap_id) && (d > 0.f);
+      if (v >= 0 && v < h && u >= 0 && u < w) {          // callers validate the crop against the image (render_data.py raises like
+        const int32_t id = id_img[(int64_t)v * w + u];    // numpy's indexing would); a grid entry outside the image is never read
+        d = depth[(int64_t)v * w + u];
+        is_bg = (id != submap_id);
+        is_fg = (id == submap_id) && (d > 0.f);
+      }
     }
     const unsigned mb = __ballot_sync(0xffffffffu, is_bg), mf = __ballot_sync(0xffffffffu, is_fg);
     if (lane == 0) { s_warp[0][wid] = __popc(mb); s_warp[1][wid] = __popc(mf); }
@@ -138,7 +140,7 @@ extern "C" int hm_crop_candidates(hm_context* ctx, const int32_t* d_id_img, cons
   HM_CHECK(d_id_img && d_depth && d_hh && d_ww && d_pix_bg && d_depth_bg && d_pix_fg && d_depth_fg && d_counts && h > 0 && w > 0 &&
                crop_h > 0 && crop_w > 0, "hm_crop_candidates: bad argument");
   if (ctx) HM_CUDA(cudaSetDevice(ctx->device));
-  crop_candidates_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_id_img, d_depth, w, submap_id, d_hh, crop_h, d_ww, crop_w, d_pix_bg, d_depth_bg,
+  crop_candidates_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_id_img, d_depth, h, w, submap_id, d_hh, crop_h, d_ww, crop_w, d_pix_bg, d_depth_bg,
                                                                d_pix_fg, d_depth_fg, d_counts);
   if (ctx) ctx->counters.kernel_launches += 1;
   HM_CUDA(cudaGetLastError());

@@ -222,12 +222,15 @@ def create_voxel_grid(decoder: Decoder, vol_dim: int = 128) -> torch.Tensor:
 # deepsdf/deep_sdf/workspace.py
 # ------------------------------------------------------------------------------------------------
 def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
-    """weight_norm(dim=0): W = v * (g / ||v||_row) (deep_sdf_decoder.py:49-54), evaluated like torch._weight_norm."""
-    v = v.float()
-    return v * (g.float().reshape(-1, 1) / v.norm(2, dim=1, keepdim=True))
+    """weight_norm(dim=0): W = v * (g / ||v||_row) (deep_sdf_decoder.py:49-54), evaluated by the very op torch's weight_norm hook
+    calls (`torch._weight_norm`), so the folded matrix is bit-identical to the `lin.weight` the reference module computes."""
+    v = v.float().contiguous()
+    return torch._weight_norm(v, g.float().reshape(-1, *([1] * (v.dim() - 1))).contiguous(), 0)
 
 
-def decoder_from_state_dict(state: dict, specs: Optional[dict] = None, device: Optional[int] = None) -> Decoder:
+def folded_weights_from_state_dict(state: dict):
+    """(W [9], b [9]) as float32 numpy arrays from a DeepSDF `model_state_dict` (keys optionally prefixed `module.`): lin0..lin7
+    carry weight-norm pairs (weight_g, weight_v) that are folded here, lin8 a plain weight (deep_sdf_decoder.py:49-56)."""
     sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in state.items()}
     W, b = [], []
     for l in range(HM_LAYERS):
@@ -237,12 +240,18 @@ def decoder_from_state_dict(state: dict, specs: Optional[dict] = None, device: O
             w = sd[f"lin{l}.weight"].cpu().float()
         W.append(w.numpy())
         b.append(sd[f"lin{l}.bias"].cpu().float().numpy())
+    return W, b
+
+
+def decoder_from_state_dict(state: dict, specs: Optional[dict] = None, device: Optional[int] = None) -> Decoder:
+    W, b = folded_weights_from_state_dict(state)
     return Decoder(W, b, device=device, specs=specs)
 
 
-def config_decoder(experiment_directory: str, checkpoint: str = "latest", device: Optional[int] = None) -> Decoder:
-    """deepsdf/deep_sdf/workspace.py:203-225: read specs.json + ModelParameters/<checkpoint>.pth, build the
-    decoder on the GPU in eval mode.  Raises like the reference when specs.json is missing."""
+def load_decoder_weights(experiment_directory: str, checkpoint: str = "latest"):
+    """The host half of config_decoder (workspace.py:203-218), no GPU needed: specs.json + ModelParameters/<checkpoint>.pth ->
+    (W [9], b [9], specs).  Raises like the reference when specs.json is missing, and for any architecture other than the
+    shipped one."""
     specs_filename = os.path.join(experiment_directory, "specs.json")
     if not os.path.isfile(specs_filename):
         raise Exception('The experiment directory does not include specifications file "specs.json"')
@@ -252,17 +261,35 @@ def config_decoder(experiment_directory: str, checkpoint: str = "latest", device
             or ns.get("xyz_in_all") or ns.get("use_tanh") or not ns.get("weight_norm")):
         raise ValueError("hortimapping_b200 supports the shipped DeepSDF architecture only (8x512, latent 32, latent_in=[4])")
     saved = torch.load(os.path.join(experiment_directory, "ModelParameters", checkpoint + ".pth"), map_location="cpu")
-    dec = decoder_from_state_dict(saved["model_state_dict"], specs, device)
-    # calibrate the tensor-core operand scales on the training codes when they are there
+    W, b = folded_weights_from_state_dict(saved["model_state_dict"])
+    return W, b, specs
+
+
+def config_decoder(experiment_directory: str, checkpoint: str = "latest", device: Optional[int] = None) -> Decoder:
+    """deepsdf/deep_sdf/workspace.py:203-225: read specs.json + ModelParameters/<checkpoint>.pth, build the
+    decoder on the GPU in eval mode.  The tensor-core engine's fp16 operand scales are calibrated on the model's own
+    training codes when LatentCodes/<checkpoint>.pth is there (else the library's synthetic default stays; `calibration`
+    says which)."""
+    W, b, specs = load_decoder_weights(experiment_directory, checkpoint)
+    dec = Decoder(W, b, device=device, specs=specs)
+    dec.calibration = "default (synthetic latents ~ N(0, 0.1))"
     lat_file = os.path.join(experiment_directory, "LatentCodes", checkpoint + ".pth")
     if os.path.isfile(lat_file):
-        codes = load_latent_vectors(experiment_directory, checkpoint).to(dec.device)
-        clamp = float(specs.get("ClampingDistance", 0.1))
-        g = torch.Generator(device="cpu").manual_seed(0)
-        n = 8192
-        z = codes[torch.randint(0, codes.shape[0], (n,), generator=g).to(dec.device)]
-        x = ((torch.rand(n, 3, generator=g) * 2 - 1) * 1.5 * clamp).to(dec.device)
-        dec.calibrate(torch.cat([z, x], 1))
+        try:
+            codes = load_latent_vectors(experiment_directory, checkpoint)
+            if isinstance(codes, (list, tuple)):          # legacy tensor-format checkpoints come back as a list (workspace.py:99-107)
+                codes = torch.stack([c.reshape(-1) for c in codes])
+            codes = codes.to(dec.device)
+            clamp = float(specs.get("ClampingDistance", 0.1))
+            g = torch.Generator(device="cpu").manual_seed(0)
+            n = 8192
+            z = codes[torch.randint(0, codes.shape[0], (n,), generator=g).to(dec.device)]
+            x = ((torch.rand(n, 3, generator=g) * 2 - 1) * 1.5 * clamp).to(dec.device)
+            dec.calibrate(torch.cat([z, x], 1))
+            dec.calibration = f"{codes.shape[0]} training codes of {lat_file}"
+        except Exception as e:                            # a broken codes file must not take the decoder down
+            import warnings
+            warnings.warn(f"hortimapping_b200: calibration on {lat_file} failed ({e}); keeping the default operand scales")
     return dec
 
 

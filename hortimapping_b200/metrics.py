@@ -57,7 +57,8 @@ class Metrics3D:
 
 
 class ChamferDistance(Metrics3D):
-    """metrics_3d/chamfer_distance.py:11-36."""
+    """metrics_3d/chamfer_distance.py:11-36: per sample the mean of the two directed mean nearest-neighbour distances
+    (an empty prediction scores 0, :17-19); `compute()` averages over the samples seen since the last `reset()`."""
 
     def __init__(self):
         self.cd_array = []
@@ -67,71 +68,69 @@ class ChamferDistance(Metrics3D):
             self.cd_array.append(0)
             return
         g, p = _points(gt), _points(pt)
-        dist_pt_2_gt = nn_distance(p, g)
-        dist_gt_2_pt = nn_distance(g, p)
-        d = (float(dist_gt_2_pt.mean().item()) + float(dist_pt_2_gt.mean().item())) / 2
-        self.cd_array.append(d)
+        both = torch.stack([nn_distance(g, p).mean(), nn_distance(p, g).mean()])      # gt -> prediction, prediction -> gt
+        self.cd_array.append(float(both.sum().item()) / 2)
 
     def reset(self):
         self.cd_array = []
 
     def compute(self):
-        return sum(self.cd_array) / len(self.cd_array)
+        return float(np.sum(self.cd_array)) / len(self.cd_array)
 
 
 class PrecisionRecall(Metrics3D):
-    """metrics_3d/precision_recall.py:11-107."""
+    """metrics_3d/precision_recall.py:11-107: precision (prediction -> ground truth), recall (ground truth -> prediction) and
+    F-score in percent at `num` distance thresholds.  One row of shape (3, num) is kept per sample; the threshold counts are
+    taken on the device, only 2 x num integers come back per sample."""
 
     def __init__(self, min_t, max_t, num):
         self.thresholds = np.linspace(min_t, max_t, num)
-        self.reset()
+        self._rows = []
 
     def update(self, gt, pt):
-        if self.prediction_is_empty(pt):
-            for t in self.thresholds:
-                self.pr_dict[t].append(0)
-                self.re_dict[t].append(0)
-                self.f1_dict[t].append(0)
+        if self.prediction_is_empty(pt):                           # :20-25: an empty prediction scores 0 everywhere
+            self._rows.append(np.zeros((3, len(self.thresholds))))
             return
         g, p = _points(gt), _points(pt)
-        dist_pt_2_gt = nn_distance(p, g)                          # precision: predicted --> ground truth
-        dist_gt_2_pt = nn_distance(g, p)                          # recall: ground truth --> predicted
-        thr = torch.from_numpy(self.thresholds).to(dist_pt_2_gt.device)
-        n_p = (dist_pt_2_gt[:, None] < thr[None, :]).sum(0).cpu().numpy()
-        n_r = (dist_gt_2_pt[:, None] < thr[None, :]).sum(0).cpu().numpy()
-        for k, t in enumerate(self.thresholds):
-            pr = 100 / len(dist_pt_2_gt) * int(n_p[k])
-            re = 100 / len(dist_gt_2_pt) * int(n_r[k])
-            self.pr_dict[t].append(pr)
-            self.re_dict[t].append(re)
-            self.f1_dict[t].append(0 if (pr == 0 or re == 0) else 2 * pr * re / (pr + re))
+        d_p, d_g = nn_distance(p, g), nn_distance(g, p)
+        thr = torch.from_numpy(self.thresholds).to(d_p.device)
+        frac = [100 / len(d) * (d[:, None] < thr[None, :]).sum(0).cpu().numpy().astype(np.float64) for d in (d_p, d_g)]
+        pr, re = frac
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f1 = np.where((pr == 0) | (re == 0), 0.0, 2 * pr * re / (pr + re))      # :44-48
+        self._rows.append(np.stack([pr, re, f1]))
 
     def reset(self):
-        self.pr_dict = {t: [] for t in self.thresholds}
-        self.re_dict = {t: [] for t in self.thresholds}
-        self.f1_dict = {t: [] for t in self.thresholds}
+        self._rows = []
+
+    def _mean(self):
+        return np.mean(np.stack(self._rows), axis=0)               # (3, num): mean over samples
+
+    def _as_dict(self, which):
+        rows = np.stack(self._rows) if self._rows else np.zeros((0, 3, len(self.thresholds)))
+        return {t: rows[:, which, k].tolist() for k, t in enumerate(self.thresholds)}
+
+    # the reference keeps three {threshold: [per-sample values]} dicts; offered read-only for host code that looks at them
+    pr_dict = property(lambda self: self._as_dict(0))
+    re_dict = property(lambda self: self._as_dict(1))
+    f1_dict = property(lambda self: self._as_dict(2))
+
+    def find_nearest_threshold(self, value):
+        return self.thresholds[int(np.argmin(np.abs(self.thresholds - value)))]
 
     def compute_at_threshold(self, threshold):
         t = self.find_nearest_threshold(threshold)
-        pr = sum(self.pr_dict[t]) / len(self.pr_dict[t])
-        re = sum(self.re_dict[t]) / len(self.re_dict[t])
-        f1 = sum(self.f1_dict[t]) / len(self.f1_dict[t])
-        return pr, re, f1, t
-
-    def compute_auc(self):
-        import scipy.integrate
-        dx = self.thresholds[1] - self.thresholds[0]
-        perfect_predictor = scipy.integrate.simpson(np.ones_like(self.thresholds), dx=dx)
-        pr, re, f1 = self.compute_at_all_thresholds()
-        return (scipy.integrate.simpson(pr, dx=dx) / perfect_predictor, scipy.integrate.simpson(re, dx=dx) / perfect_predictor,
-                scipy.integrate.simpson(f1, dx=dx) / perfect_predictor)
+        k = int(np.argmin(np.abs(self.thresholds - threshold)))
+        pr, re, f1 = self._mean()[:, k]
+        return float(pr), float(re), float(f1), t
 
     def compute_at_all_thresholds(self):
-        pr = [sum(self.pr_dict[t]) / len(self.pr_dict[t]) for t in self.thresholds]
-        re = [sum(self.re_dict[t]) / len(self.re_dict[t]) for t in self.thresholds]
-        f1 = [sum(self.f1_dict[t]) / len(self.f1_dict[t]) for t in self.thresholds]
-        return pr, re, f1
+        m = self._mean()
+        return m[0].tolist(), m[1].tolist(), m[2].tolist()
 
-    def find_nearest_threshold(self, value):
-        idx = (np.abs(self.thresholds - value)).argmin()
-        return self.thresholds[idx]
+    def compute_auc(self):
+        """Area under the three curves over the threshold range, normalised by the area of a perfect predictor (:69-90)."""
+        from scipy.integrate import simpson
+        dx = self.thresholds[1] - self.thresholds[0]
+        unit = simpson(np.ones_like(self.thresholds), dx=dx)
+        return tuple(float(simpson(c, dx=dx) / unit) for c in self._mean())

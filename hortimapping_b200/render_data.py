@@ -59,11 +59,29 @@ class _Frame:
 _frames: "dict[tuple, _Frame]" = {}
 
 
+def _fingerprint(a: np.ndarray):
+    """Cheap content guard of the frame cache: shape, dtype and a strided sample of the pixels (an image that is modified in
+    place, or a new array that reuses a dead one's id(), must not be served from a stale device copy)."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.shape[0] // 4096)
+    return (a.shape, str(a.dtype), hash(flat[::step].tobytes()))
+
+
+def clear_frame_cache():
+    """Drops every cached device copy of frames (they are otherwise dropped with their host arrays)."""
+    _frames.clear()
+
+
 def _frame_of(id_img, depth_img, dev) -> _Frame:
     key = (id(id_img), id(depth_img), str(dev))
+    fp = (_fingerprint(id_img), _fingerprint(depth_img))
     fr = _frames.get(key)
+    if fr is not None and fr.fingerprint != fp:
+        fr = None
     if fr is None:
         fr = _Frame(id_img, depth_img, dev)
+        fr.fingerprint = fp
         _frames[key] = fr
         for obj in (id_img, depth_img):                                      # drop the device copy with the host image
             try:
@@ -119,6 +137,10 @@ def get_render_data(submap_id, id_imgs, depth_imgs, cam_poses, img_size, invK, c
         hh = np.linspace(min_v, max_v, int(bbx_h / down_rate)).astype(np.int32)       # :65-66 (fp64 linspace, truncated)
         ww = np.linspace(min_u, max_u, int(bbx_w / down_rate)).astype(np.int32)
         crop_h, crop_w = hh.shape[0], ww.shape[0]
+        if crop_h and crop_w and (int(hh.max()) >= fr.h or int(ww.max()) >= fr.w):
+            # img_size from the config exceeds the uploaded image: the reference's numpy indexing raises here, so does this
+            raise IndexError(f"crop row {int(hh.max())} / column {int(ww.max())} is outside the {fr.h} x {fr.w} image of frame {img_id} "
+                             f"(img_size = {tuple(img_size)})")
         n = crop_h * crop_w
         st = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):

@@ -15,8 +15,10 @@
  *     Nothing is thrown across the ABI.  Per-fruit data problems are NOT errors: they are reported in
  *     the status words (HM_STATUS_*), mirroring the reference's print-and-continue behaviour
  *     (wild_completion/optimizer.py:130-141).
- *   - a context is bound to one device, owns the split-precision copies of the decoder weights and a
- *     grow-only workspace, and is not thread-safe.
+ *   - a context is bound to one device and owns the split-precision copies of the decoder weights and grow-only scratch that
+ *     every call reuses.  Calls of one context are therefore serialised on the GPU even across streams (a call issued on
+ *     another stream than the previous one first waits, device-side, for that call's work); use one context per stream for
+ *     concurrency.  A context is not thread-safe: calls from several host threads need external locking.
  */
 #ifndef HORTIMAPPING_B200_H
 #define HORTIMAPPING_B200_H

@@ -106,3 +106,29 @@ def test_fused_grid_equals_explicit_points_and_full_size_grid():
     # are taken at sheared positions but meshed as a regular grid -- a few millimetres at this resolution)
     s = dec.sdf(lat, v).abs().max()
     assert float(s) < 0.005
+
+
+@pytest.mark.parametrize("n", [40, 128])
+def test_device_isosurface_coincides_with_marching_cubes(n):
+    """N2 at surface level (wild_completion/utils.py:565-588): the reference runs skimage's marching cubes on the N^3 grid; the
+    device extractor (marching tetrahedra) must give the same surface.  Both are extracted from the SAME device SDF grid of the
+    shipped model (40^3 = the shipped configs' grid, 128^3 = BASELINE.json configs[0]) and compared by exact point-to-triangle
+    distances in voxel units: symmetric mean (Chamfer) < 0.1 voxel, as VERDICT r01 item 8 asks."""
+    import torch
+    from oracle import marching_cubes as MC
+    from tests.gpu_helpers import pepper_decoder
+    from tests.helpers import pepper_weights, point_to_mesh_distance
+    dec = pepper_decoder()
+    _, _, codes = pepper_weights()
+    lat = torch.from_numpy(codes[5]).cuda()
+    sdf = dec.sdf_grid(lat, n, 0.08)
+    h = 2.0 / (n - 1)
+    vd, fd = dec.isosurface(sdf, 0.0, h)
+    vd, fd = vd.cpu().numpy().astype(np.float64), fd.cpu().numpy()
+    vc, fc = MC.marching_cubes(sdf.cpu().numpy(), 0.0, (h,) * 3)
+    assert len(fd) > 1000 and len(fc) > 1000
+    d1 = point_to_mesh_distance(vd, vc, fc) / h
+    d2 = point_to_mesh_distance(vc, vd, fd) / h
+    chamfer = 0.5 * (d1.mean() + d2.mean())
+    assert chamfer < 0.1 and max(d1.max(), d2.max()) < 1.0, (chamfer, d1.max(), d2.max())
+    print(f"{n}^3: {len(fd)} device faces vs {len(fc)} marching-cubes faces, Chamfer {chamfer:.4f} voxel, max {max(d1.max(), d2.max()):.3f} voxel")

@@ -9,6 +9,8 @@ import torch
 
 from tests.helpers import cfg_of, load_npz, render_data_of
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_opt_params_mirror_reference_config_reads():
     from hortimapping_b200.optimizer import opt_params_from_cfg
@@ -153,3 +155,45 @@ def test_metric_input_conversion_and_bookkeeping_without_gpu():
     pr.update(a, torch.zeros(0, 3))                                  # precision_recall.py:20-25
     assert cd.compute() == 0 and pr.compute_at_threshold(0.005)[:3] == (0, 0, 0)
     assert pr.find_nearest_threshold(0.0049) == pr.thresholds[4]
+
+
+def _model_dirs():
+    out = []
+    for base in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        for model in ("sweetpepper_32", "strawberry_32"):
+            d = os.path.join(base, "deepsdf", "models", model)
+            if os.path.isfile(os.path.join(d, "ModelParameters", "latest.pth")):
+                out.append((model, d))
+        if out:
+            break
+    return out
+
+
+@pytest.mark.parametrize("model,model_dir", _model_dirs() or [pytest.param(None, None, marks=pytest.mark.skip(reason="no shipped checkpoint reachable"))])
+def test_product_checkpoint_loader_matches_the_reference_module(model, model_dir):
+    """a2 (workspace.py:82-114,203-225): the product's own loader -- specs check, weight-norm folding, latent codes -- run on the
+    SHIPPED .pth files must reproduce the weights the unmodified reference module materialises (tests/golden/<model>.npz was
+    exported from `lin.weight` of the reference's Decoder after its weight_norm pre-forward hook, oracle/gen_golden.py)."""
+    from hortimapping_b200.decoder import load_decoder_weights, load_latent_vectors
+    from tests.helpers import load_npz
+    W, b, specs = load_decoder_weights(model_dir, "latest")
+    z = load_npz(model)
+    assert specs["CodeLength"] == 32
+    for l in range(9):
+        assert W[l].dtype == np.float32 and W[l].shape == z[f"W{l}"].shape
+        np.testing.assert_array_equal(W[l], z[f"W{l}"])                      # same op as torch's weight_norm hook: bit-identical
+        np.testing.assert_array_equal(b[l], z[f"b{l}"])
+    codes = load_latent_vectors(model_dir, "latest")
+    np.testing.assert_array_equal(codes.numpy(), z["latent_codes"])
+
+
+def test_checkpoint_loader_errors(tmp_path):
+    from hortimapping_b200.decoder import load_decoder_weights, load_latent_vectors
+    with pytest.raises(Exception, match="specs.json"):
+        load_decoder_weights(str(tmp_path))
+    import json
+    json.dump({"CodeLength": 64, "NetworkSpecs": {"dims": [512] * 8, "latent_in": [4], "weight_norm": True}}, open(tmp_path / "specs.json", "w"))
+    with pytest.raises(ValueError, match="shipped DeepSDF architecture"):
+        load_decoder_weights(str(tmp_path))
+    with pytest.raises(Exception, match="latent code file"):
+        load_latent_vectors(str(tmp_path))
