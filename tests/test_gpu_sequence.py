@@ -56,6 +56,8 @@ def test_unchanged_host_script_runs_on_a_synthetic_bup20_sequence(tmp_path):
         report.append((int(fid), float(s / s_gt), float(e_t), float(chamfer)))
     print(f"sequence of {len(report)} fruits completed in {wall:.1f} s wall (process start, model load and image IO included): "
           + "; ".join(f"id {i}: scale ratio {a:.3f}, |dt| {b * 1e3:.1f} mm, chamfer {c * 1e3:.2f} mm" for i, a, b, c in report))
-    # partial view (front half only), 30 LM iterations, 4 mm mesher voxels: the completed fruit must sit where the hidden truth is
+    # Partial view (front half only), 30 LM iterations, 4 mm mesher voxels: the completed fruit must sit where the hidden truth is.
+    # The Sim(3) scale itself is not identifiable (the latent space also encodes size: a larger shape at a smaller scale is the
+    # same surface), so it is reported and only loosely bounded; the surface distance and the position carry the check.
     for fid, ratio, e_t, chamfer in report:
-        assert abs(ratio - 1) < 0.15 and e_t < 0.015 and chamfer < 0.008, report
+        assert 0.5 < ratio < 1.5 and e_t < 0.015 and chamfer < 0.008, report
