@@ -149,9 +149,9 @@ extern "C" int hm_set_engine(hm_context* ctx, int engine) {
 
 extern "C" int hm_get_engine(const hm_context* ctx) { return ctx ? ctx->engine : HM_ERR_INVALID; }
 
-extern "C" int hm_set_zero_shortcut(hm_context* ctx, int on) {
-  HM_CHECK(ctx, "hm_set_zero_shortcut: null context");
-  ctx->zero_shortcut = on ? 1 : 0;
+extern "C" int hm_set_sparse_plan(hm_context* ctx, int on) {
+  HM_CHECK(ctx, "hm_set_sparse_plan: null context");
+  ctx->sparse_plan = on ? 1 : 0;
   return HM_OK;
 }
 
@@ -180,8 +180,8 @@ extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
     out->rows_jacobian += (int64_t)dev[1];
     out->tiles_forward = (int64_t)dev[2];
     out->tiles_jacobian = (int64_t)dev[3];
-    out->tiles_dead_forward = (int64_t)dev[4];
-    out->tiles_dead_jacobian = (int64_t)dev[5];
+    out->tiles_redone_forward = (int64_t)dev[4];
+    out->tiles_redone_jacobian = (int64_t)dev[5];
   }
   return HM_OK;
 }
@@ -214,10 +214,12 @@ extern "C" int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, voi
   // sdf output is discarded: put it at the end of a scratch allocation
   float* d_sdf = nullptr;
   HM_CUDA(cudaMalloc(&d_sdf, sizeof(float) * n));
-  int rc = hm_simt_decode(ctx, rows, d_sdf, nullptr, (cudaStream_t)stream, absmax);
+  std::vector<float> unit_max(8 * HM_HIDDEN, 0.f);
+  int rc = hm_simt_decode(ctx, rows, d_sdf, nullptr, (cudaStream_t)stream, absmax, unit_max.data());
   cudaFree(d_sdf);
   if (rc) return rc;
   for (int i = 0; i < 16; ++i) ctx->act_absmax[i] = absmax[i];
+  ctx->unit_max = unit_max;
   return hm_tc_init(ctx);
 }
 

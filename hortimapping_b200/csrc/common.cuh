@@ -43,29 +43,40 @@ void hm_set_error(const char* fmt, ...);
 #define HM_TC_STAGE_N 256        // weight rows (output features) per pipeline stage (64 for B0); a CTA pair splits them
 #define HM_TC_CHUNK_K 64         // K extent of one 128-byte swizzle atom row (fp16)
 
+// int32 slots of hm_context::d_tc_flags (device counters of the tensor-core engine; 64-bit totals take two slots)
+#define HM_TC_FLAG_SAT 0            // saturation events: (tile, thread) pairs in which an fp16 operand conversion saturated
+#define HM_TC_FLAG_ROWS_FWD 2       // rows evaluated by forward-only launches
+#define HM_TC_FLAG_ROWS_JAC 4       // rows evaluated by forward + input-gradient launches
+#define HM_TC_FLAG_TILES_FWD 6      // 64-row tiles processed (forward-only / forward + gradient)
+#define HM_TC_FLAG_TILES_JAC 8
+#define HM_TC_FLAG_DEAD_FWD 10      // ... of which failed the sparse plan's checks and were re-evaluated with the full plan
+#define HM_TC_FLAG_DEAD_JAC 12
+#define HM_TC_FLAG_DEBUG 32         // wait-cycle counters of the instrumented testing build (HM_TC_COUNTERS)
+#define HM_TC_FLAG_COUNT 128
+
 struct hm_tc_op {
   int32_t n_kchunks;             // K / 64 of the A operand (1 for F0, 8 otherwise)
   int32_t n_nblocks;             // output halves of stage_rows columns (2; 1 for B0)
   int32_t stage_rows;            // weight rows per stage = MMA N (256; 64 for B0)
-  int32_t pad_;
+  // Sparse plan: hidden units are permuted so that the units calibration saw alive come first, which makes
+  // whole 64-wide k-chunks of the activations exactly zero.  The masks below say what is still multiplied / produced; a tile for
+  // which a forward op finds a non-zero outside `verify_alive` is re-evaluated with the full plan (all masks 0xFF).
+  uint8_t chunk_mask;            // k-chunks of the A operand that are multiplied (bit c = chunk c); 0 = the op is dropped
+  uint8_t half_mask;             // output halves that are computed (bit nh)
+  uint8_t group_mask;            // = the accumulation groups issued, in issue order (derived from the two masks above)
+  uint8_t need_out;              // output chunks the epilogue has to produce (what the next executed op multiplies / the final result)
+  uint8_t verify_alive;          // forward ops: output chunks that may hold non-zeros after the ReLU (0xFF = no assumption)
+  uint8_t is_last;               // backward ops: the last executed op of the gradient pass writes the final Jacobian rows
+  uint8_t pad_[2];
   float in_scale;                // power of two applied to the A operand before the fp16 split
   float out_unscale;             // 1 / (in_scale * w_scale): turns the accumulator back into fp32 units
   int64_t blob_offset;           // byte offset of this op's first stage in the weight blob
 };
 
-// int32 slots of hm_context::d_tc_flags (device counters of the tensor-core engine; 64-bit totals take two slots)
-#define HM_TC_FLAG_SAT 0            // thread blocks in which an fp16 operand conversion saturated
-#define HM_TC_FLAG_ROWS_FWD 2       // rows evaluated by forward-only launches
-#define HM_TC_FLAG_ROWS_JAC 4       // rows evaluated by forward + input-gradient launches
-#define HM_TC_FLAG_TILES_FWD 6      // 64-row tiles processed (forward-only / forward + gradient)
-#define HM_TC_FLAG_TILES_JAC 8
-#define HM_TC_FLAG_DEAD_FWD 10      // ... of which took the zero-operand shortcut
-#define HM_TC_FLAG_DEAD_JAC 12
-#define HM_TC_FLAG_DEBUG 32         // wait-cycle counters of the instrumented debug build (HM_TC_COUNTERS)
-#define HM_TC_FLAG_COUNT 128
-
 struct hm_tc_plan {
   hm_tc_op ops[HM_TC_NOPS_ALL];
+  int32_t last_op_fwd, last_op_jac;     // last executed op of a forward-only / forward + gradient pass
+  int32_t sparse;                       // 1: some mask is not full, i.e. tiles can fail the checks and need the full plan
 };
 
 struct hm_context {
@@ -83,14 +94,19 @@ struct hm_context {
   uint8_t* d_tc_blob = nullptr;    // pre-swizzled fp16 hi/lo weight stages for all 16 ops
   size_t tc_blob_bytes = 0;
   int tc_blob_copies = 1;
-  hm_tc_plan tc_plan;
+  hm_tc_plan tc_plan;              // the sparse plan (== the full plan for a model without dead units)
+  hm_tc_plan tc_plan_full;         // every mask full: the reference evaluation, used for the tiles that fail the sparse plan's checks
+  int32_t* d_tc_redo = nullptr;    // [0] = number of queued tiles, [4 ..] = their indices (grow-only)
+  size_t tc_redo_cap = 0;
+  float* d_w8p = nullptr;          // lin8 weight in the permuted unit order of the tensor-core engine
   float act_absmax[HM_TC_NOPS_ALL] = {};   // calibration result: max |A operand| per op
+  std::vector<float> unit_max;             // calibration result: [8][512] largest activation of every hidden unit (0 = never alive)
   float* d_tc_bias = nullptr;      // [8][512] biases of lin0..7 (lin3 padded with 0)
   float* d_w8 = nullptr;           // [512] lin8 weight, d_b8 scalar in d_b[8]
   uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
   int32_t* d_tc_flags = nullptr;   // saturation counter etc.
   uint32_t* d_tc_trace = nullptr;  // timeline buffer of the instrumented testing build (NULL in the product)
-  int zero_shortcut = 1;           // tensor-core engine: skip MMAs with an exactly-zero A operand (dead lin3), hm_set_zero_shortcut
+  int sparse_plan = 1;             // tensor-core engine: use the calibrated sparse plan (hm_set_sparse_plan); 0 = full plan always
   // grow-only workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -178,7 +194,7 @@ __device__ __forceinline__ float hm_grid_coord(int64_t i, int c, int n, float vo
 }
 
 int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st,
-                   float* h_absmax_out /* [16] or NULL: calibration */);
+                   float* h_absmax_out /* [16] or NULL: calibration */, float* h_unit_max_out = nullptr /* [8][512] or NULL */);
 int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st);
 int hm_tc_init(hm_context* ctx);          // build weight blob + plan from ctx->h_W and act_absmax
 void hm_tc_free(hm_context* ctx);

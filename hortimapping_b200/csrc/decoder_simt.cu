@@ -127,6 +127,15 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
   if (threadIdx.x % 32 == 0) atomicMax((int*)out, __float_as_int(m));   // non-negative floats order as ints
 }
 
+// per-column maximum of a row-major [n][ncol] matrix of non-negative values (post-ReLU activations): which hidden units were ever alive
+__global__ void colmax_kernel(const float* __restrict__ x, int64_t n, int ncol, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  float m = 0.f;
+  for (int64_t r = blockIdx.y; r < n; r += gridDim.y) m = fmaxf(m, x[r * ncol + c]);
+  atomicMax((int*)(out + c), __float_as_int(m));   // non-negative floats order as ints
+}
+
 template <bool B_NK>
 void launch_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int64_t n,
                  int N, int K, int epi, const float* aux, int ld_aux, cudaStream_t st) {
@@ -137,11 +146,11 @@ void launch_gemm(const float* A, int lda, const float* B, int ldb, const float* 
 }  // namespace
 
 int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st,
-                   float* h_absmax_out) {
+                   float* h_absmax_out, float* h_unit_max_out) {
   const int64_t CH = 16384;
   const bool want_jac = d_jac != nullptr || h_absmax_out != nullptr;
   // workspace: rows35 [CH][35] (padded to 36), h[8][CH][512], d ping-pong [2][CH][512], absmax[16]
-  size_t bytes = sizeof(float) * (CH * 36 + (size_t)8 * CH * HM_HIDDEN + (size_t)2 * CH * HM_HIDDEN + 64 + CH * HM_IN);
+  size_t bytes = sizeof(float) * (CH * 36 + (size_t)8 * CH * HM_HIDDEN + (size_t)2 * CH * HM_HIDDEN + 64 + CH * HM_IN + 8 * HM_HIDDEN);
   int rc = hm_ws_reserve(ctx, bytes);
   if (rc) return rc;
   float* w = (float*)ctx->ws;
@@ -151,8 +160,10 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
   float* dA = w; w += CH * HM_HIDDEN;
   float* dB = w; w += CH * HM_HIDDEN;
   float* amax = w; w += 64;
-  float* jac_tmp = w;
+  float* jac_tmp = w; w += CH * HM_IN;
+  float* unit_max = w;                   // [8][512]: per hidden unit, the largest activation seen (calibration only)
   if (h_absmax_out) HM_CUDA(cudaMemsetAsync(amax, 0, 64 * sizeof(float), st));
+  if (h_unit_max_out) HM_CUDA(cudaMemsetAsync(unit_max, 0, 8 * HM_HIDDEN * sizeof(float), st));
   int64_t n_total = rows.n;
   if (rows.d_n_dynamic) {   // validation engine: a host read-back of the device-side row count is acceptable here
     int32_t nd = 0;
@@ -185,6 +196,8 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
       launch_gemm<true>(h[l - 1], HM_HIDDEN, ctx->d_W[l], HM_HIDDEN, ctx->d_b[l], h[l], HM_HIDDEN, n, HM_HIDDEN, HM_HIDDEN,
                         epi, x0, HM_IN, st);
     }
+    if (h_unit_max_out)
+      for (int l = 0; l < 8; ++l) colmax_kernel<<<dim3(HM_HIDDEN / 128, 64), 128, 0, st>>>(h[l], n, HM_HIDDEN, unit_max + l * HM_HIDDEN);
     head_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h[7], ctx->d_W[8], ctx->d_b[8], n, rows.d_out_index ? d_sdf : d_sdf + r0,
                                                          rows.d_out_index ? rows.d_out_index + r0 : nullptr, want_jac ? dA : nullptr,
                                                          h_absmax_out ? 1 : 0);
@@ -209,6 +222,7 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
                        HM_HIDDEN, st);
   }
   HM_CUDA(cudaGetLastError());
+  if (h_unit_max_out) HM_CUDA(cudaMemcpyAsync(h_unit_max_out, unit_max, 8 * HM_HIDDEN * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_absmax_out) {
     HM_CUDA(cudaMemcpyAsync(h_absmax_out, amax, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     HM_CUDA(cudaStreamSynchronize(st));

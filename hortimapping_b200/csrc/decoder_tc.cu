@@ -19,11 +19,13 @@
 //     one of four TMEM buffers, and the group partials are summed in registers in fp32 round-to-nearest.
 //   * the backward pass is seeded with w8 * relu'(h7) as soon as lin7's output half is final; the tanh' factor (1 - sdf^2) is a
 //     per-row scalar and multiplies the finished gradient, so lin8 + tanh are off the tensor core's critical path.
-//   * zero-operand shortcut: when every lin3 output of a tile PAIR is 0 after the ReLU (true for every row of both shipped
-//     models: lin3 is dead, the network lives on the skip connection) the MMAs whose A operand is exactly zero are not issued:
-//     lin4 reads only the k-step that carries the skip-concat columns, the gradient stops at lin4's skip columns (B4 computes only
-//     its upper output half, B3..B0 are dropped).  The pair decides per tile from its own ReLU bits (one flag exchanged through
-//     distributed shared memory); the skipped products are exact zeros, so the results are bit-identical to the full evaluation.
+//   * sparse plan: the shipped DeepSDF models are extremely sparse after their ReLUs (lin3 is dead outright -- the network lives
+//     on the skip connection -- and only 12 .. 320 of the 512 units of the other layers are ever alive).  hm_calibrate records
+//     which units were alive, the hidden units are permuted so that those come first, and the plan drops every MMA whose A
+//     operand is then an all-zero 64-wide k-chunk (and every output half nobody reads in the gradient pass).  The assumption is
+//     CHECKED, not trusted: each forward layer's epilogue looks at the ReLU bits of the columns the plan counts on being zero and
+//     a tile that contradicts it is queued and re-evaluated by a second launch of the same kernel with the full plan.  The
+//     dropped products are exact zeros, so sparse == full bit for bit.
 //
 // Warp roles (640 threads): warpgroup 0 = control (warp 0 bulk-copy producer, warp 1 MMA issuer in the leader CTA / weight
 // arrival forwarder in the peer CTA + TMEM alloc, warps 2-3 idle), warpgroups 1-4 = 16 epilogue warps (4 per TMEM
@@ -58,12 +60,10 @@ constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per f
 
 // barrier slots (8 bytes each) inside the 256-byte control block at kSmemBars, followed by a few control words
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = kMaxStages, BAR_A_READY = 2 * kMaxStages, BAR_PART_FULL = BAR_A_READY + 4,
-       BAR_PART_EMPTY = BAR_PART_FULL + 4, BAR_DEAD = BAR_PART_EMPTY + 4, BAR_COUNT = BAR_DEAD + 1 };
+       BAR_PART_EMPTY = BAR_PART_FULL + 4, BAR_COUNT = BAR_PART_EMPTY + 4 };
 constexpr int kCtlTmemPtr = 8 * BAR_COUNT;         // TMEM base column written by tcgen05.alloc
-constexpr int kCtlAlive = kCtlTmemPtr + 4;         // set by any epilogue warp of this CTA that saw a live lin3 output in the current tile
-constexpr int kCtlFlagOwn = kCtlTmemPtr + 8;       // [2] this CTA's "some lin3 output is alive" flag of tile parity 0 / 1
-constexpr int kCtlFlagPeer = kCtlTmemPtr + 16;     // [2] the peer CTA's flag, stored remotely by the peer
-static_assert(kCtlFlagPeer + 8 <= 256, "control block overflows into the bias / dot-product scratch");
+constexpr int kCtlViolated = kCtlTmemPtr + 4;      // set by an epilogue warp whose tile contradicted the sparse plan
+static_assert(kCtlViolated + 4 <= 256, "control block overflows into the bias / dot-product scratch");
 
 struct TcParams {
   hm_tc_plan plan;
@@ -88,7 +88,7 @@ struct TcParams {
   uint32_t* trace;            // timeline of the first CTA pair (testing build only) or null
   int32_t grid_n;             // > 0: xyz of row i = voxel grid point i (fused mesher grid, hm_rows)
   float grid_voxel, grid_radius;
-  int32_t zero_shortcut;      // 1: skip the MMAs whose A operand is exactly zero when a tile pair's lin3 output is all zero
+  int32_t* redo;              // [0] = number of queued tiles, [4 ..] = tile indices: appended by the sparse pass, read by the redo pass
 };
 
 // k-chunk order of an 8-chunk op: k-step s multiplies chunks {0,2}, {1,3}, {4,6}, {5,7}.  Steps 0,1 read the chunks that the
@@ -106,31 +106,35 @@ __host__ __device__ __forceinline__ void group_of(int n_kchunks, int n_nblocks, 
   else { step = (0x32321100u >> (4 * g)) & 0xF; nh = (0xCAu >> g) & 1; }
 }
 
-// Zero-operand shortcut: the groups of op `op` (bit g = group g in issue order) that are still issued for a tile pair whose lin3
-// output is all zero ("dead").  F4 (op 4) reads h3 ++ x0: only k-step 3 (chunks 5 and 7) is kept, and of it only chunk 7, which
-// carries the skip-concat columns 477..511.  B4 (op 11) produces d(h3 ++ x0): only its upper output half, which holds the
-// skip-gradient columns, is kept; the lower half and everything behind it (B3..B0, ops 12..15) would be multiplied by
-// relu'(h3) = 0.
-__device__ __forceinline__ uint32_t issued_groups(int op, bool dead) {
-  if (!dead) return 0xFFu;
-  if (op == 4) return 0xA0u;          // (3,0) and (3,1)
-  if (op == 11) return 0xCAu;         // the four nh = 1 groups
-  return op >= 12 ? 0u : 0xFFu;
+// Sparse plan (common.cuh hm_tc_op): is stage (step, which) of an op multiplied?
+__device__ __forceinline__ bool stage_used(const hm_tc_op& o, int step, int which) {
+  const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+  return (o.chunk_mask >> chunk) & 1u;
 }
 
 // The kernel runs as clusters of two CTAs (one TPC).  Each CTA owns a tile of 64 points; the pair issues cta_group::2 MMAs
-// of M = 128 (64 rows per CTA -- measured: full rate, 64 cycles for N = 256, scripts/probe_pair.py) whose B operand is
+// of M = 128 (64 rows per CTA -- measured: full rate, 64 cycles for N = 256, scripts/probe_decoder.py pair) whose B operand is
 // split between the two CTAs' shared memories, so each CTA streams only HALF of every weight tile from L2.  Per weight
 // tile pair the THREE needed products are issued -- A_hi x W_lo, A_lo x W_hi, A_hi x W_hi -- into the same accumulator
 // rows (the 64 x N accumulator of each CTA is folded onto 128 lanes x N/2 columns: lanes 0..63 hold output columns
 // [0, N/2), lanes 64..127 columns [N/2, N)).  CTA rank 0 (the leader) issues all MMAs.
-template <bool kJac>
+//
+// kRedo = false: tiles 2 * unit + rank, evaluated with P.plan (the sparse plan); a tile whose activations contradict the
+// plan's zero-chunk assumptions is appended to P.redo.  kRedo = true: the tiles listed in P.redo, evaluated with P.plan = the
+// full plan (launched right behind the first kernel; exits at once when the list is empty).
+template <bool kJac, bool kRedo>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int CG = 2;
   constexpr int kStages = kMaxStages;
   constexpr int kStageBytes = kWeightRing / kStages;      // 128 output features x 64 k x 2 B (hi OR lo) = this CTA's half of a tile
   constexpr bool kPair = true;
+  const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
+  int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
+  if (kRedo) {
+    n_tiles = P.redo[0];                                  // tiles queued by the sparse pass (uniform over the grid)
+    if (n_tiles == 0) return;
+  }
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp index as a uniform value
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + kSmemBars;
@@ -140,16 +144,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups] (lin8 tail) ...
   float* bias_s = dot_scratch;                                                // ... and, before it, the current forward op's 512 biases
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
+  const int last_op = kJac ? P.plan.last_op_jac : P.plan.last_op_fwd;         // last executed op of a tile
   const uint32_t rank = cluster_ctarank();                                    // 0 = leader (MMA issuer) of the pair
   const uint32_t lead_bars = mapa_rank(bars, 0);                              // the leader's barrier block (cluster address)
   auto lead_bar = [&](int i) { return lead_bars + 8u * i; };
   const int64_t unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
-  const bool shortcut = P.zero_shortcut != 0;
 #ifdef HM_TESTING
   // timeline of the first CTA pair: (code << 24 | op << 16 | index, clock) pairs; region 0 = MMA issuer, 1 / 2 = first
-  // epilogue warp of the leader / peer CTA (scripts/probe_trace.py)
+  // epilogue warp of the leader / peer CTA (scripts/probe_decoder.py trace)
   constexpr uint32_t kTraceCap = 8192;
-  const bool tracing = P.trace != nullptr && blockIdx.x < 2;
+  const bool tracing = P.trace != nullptr && blockIdx.x < 2 && !kRedo;
   uint32_t trace_n = 0;
   auto trace = [&](int region, uint32_t code, uint32_t op, uint32_t idx) {
     if (tracing && trace_n < kTraceCap) {
@@ -169,8 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), rank == 0 ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
     for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG / 2);      // a k-step's chunks come from half of the warps
     for (int b = 0; b < kBufs; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
-    mbar_init(bar(BAR_DEAD), 2);                             // this CTA's and the peer's lin3 flag of the tile have been written
-    ctl[kCtlAlive / 4] = 0u;
+    ctl[kCtlViolated / 4] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(smem_u32((const void*)tmem_ptr_smem), 512);
@@ -181,22 +184,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (lane == 0 && (warp == 1 || warp == kCtrlWarps)) HM_TRACE(warp == 1 ? 0 : 1 + rank, 0, 0, 0);     // common time origin
 
-  const int64_t n_rows = P.n_dynamic ? (int64_t)min((int64_t)*P.n_dynamic, P.n) : P.n;
-  const int64_t n_tiles = (n_rows + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {     // exact row / tile accounting for the roofline (rows actually evaluated)
+  if (!kRedo && blockIdx.x == 0 && threadIdx.x == 0) {     // exact row / tile accounting for the roofline (rows actually evaluated)
     atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_ROWS_JAC : HM_TC_FLAG_ROWS_FWD)), (unsigned long long)n_rows);
     atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_TILES_JAC : HM_TC_FLAG_TILES_FWD)), (unsigned long long)n_tiles);
   }
+  if (kRedo && blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_DEAD_JAC : HM_TC_FLAG_DEAD_FWD)), (unsigned long long)n_tiles);
   const int64_t n_units = (n_tiles + 1) / 2;               // a unit = one tile per CTA of the pair
-
-  // "is this tile pair dead?" -- read by every role after the epilogue warps of both CTAs have published their flags (BAR_DEAD,
-  // one phase per tile).  All lanes of the calling warp wait, so the result is warp-uniform.
-  auto wait_dead_flag = [&](uint32_t tile_seq) -> bool {
-    const uint32_t par = tile_seq & 1u;
-    mbar_wait_acq_cluster(bar(BAR_DEAD), par);
-    const uint32_t any_alive = ctl[kCtlFlagOwn / 4 + par] | ctl[kCtlFlagPeer / 4 + par];
-    return shortcut && any_alive == 0u;
-  };
 
   if (warp < kCtrlWarps) {
   // the control warpgroup hands most of its registers to the four epilogue warpgroups (64 accumulators per thread)
@@ -204,25 +198,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   if (warp == 0 || (warp == 1 && rank != 0)) {
     // ===================== warp 0: weight producer (every CTA fetches its half of each stage) =====================
     // ===================== warp 1 of the peer CTA: tells the leader that this CTA's half of a stage has landed =====================
-    // Both walk the same stage sequence: the stages of the groups that are issued (issued_groups), in the blob's order.
+    // Both walk the same stage sequence: the stages of the groups that the plan issues, in the blob's (consumption) order.
     const bool producer = warp == 0;
-    uint32_t slot = 0, phase = 0, tile_seq = 0;
+    uint32_t slot = 0, phase = 0;
     long long t_empty = 0;
-    for (int64_t unit = unit0; unit < n_units; unit += unit_stride, ++tile_seq) {
-      bool dead = false;
+    for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
       for (int op = 0; op < kOps; ++op) {
         const hm_tc_op& o = P.plan.ops[op];
-        if (op == 4) dead = wait_dead_flag(tile_seq);
-        const uint32_t gm = issued_groups(op, dead);
+        const uint32_t gm = o.group_mask;
+        if (gm == 0u) continue;
         const uint32_t bytes = (uint32_t)o.stage_rows * 128u / CG;     // this CTA's rows of one 64-k fp16 tile
         const int ng = groups_of(o.n_kchunks, o.n_nblocks);
         const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
         const uint8_t* src = P.blob + o.blob_offset + (size_t)rank * bytes;
         for (int g = 0; g < ng; ++g) {
           if (!((gm >> g) & 1u)) continue;
+          int step, nh;
+          group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
           for (int part = 0; part < 2; ++part)
             for (int which = 0; which < nwhich; ++which) {
-              if (dead && op == 4 && which == 0) continue;               // chunk 5 of the dead F4 is all zero as well
+              if (!stage_used(o, step, which)) continue;
               const int s = (g * 2 + part) * nwhich + which;             // stage index inside the op (consumption order)
               if (producer) {
                 mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
@@ -249,25 +244,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       // and A_hi x W_hi (8 MMAs), each M = 64 per CTA x N = 256 x K = 16, into a FRESH 128-column TMEM buffer (four buffers).
       // The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA), so chains are
       // kept to one group and the epilogue warps add the group partials in fp32 round-to-nearest.
-      uint32_t slot = 0, phase = 0, a_seq = 0, gseq = 0, tile_seq = 0;
+      uint32_t slot = 0, phase = 0, a_seq = 0, gseq = 0;
       long long t_a = 0, t_part = 0, t_w = 0;
 #ifdef HM_TC_COUNTERS
       const long long t_begin = clock64();
 #endif
-      for (int64_t unit = unit0; unit < n_units; unit += unit_stride, ++tile_seq) {
-        bool dead = false;
+      for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
         for (int op = 0; op < kOps; ++op) {
           const hm_tc_op& o = P.plan.ops[op];
-          if (op == 4) dead = wait_dead_flag(tile_seq);
-          const int ng = groups_of(o.n_kchunks, o.n_nblocks);
-          const uint32_t gm = issued_groups(op, dead) & ((1u << ng) - 1u);
-          if (gm == 0u) continue;                  // op dropped: the epilogue warps produced no A operand (and no A_READY phase) for it
+          const uint32_t gm = o.group_mask;
+          if (gm == 0u) continue;                  // op dropped by the plan: the epilogue warps produce no A operand (and no A_READY phase) for it
           const uint32_t a_par = a_seq & 1u;       // A_READY completes one phase per executed op
           ++a_seq;
           const uint32_t idesc = make_idesc(64 * CG, o.stage_rows);
+          const int ng = groups_of(o.n_kchunks, o.n_nblocks);
           const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
           int steps_ready = 0;
-          if (o.n_kchunks == 1 || (dead && op == 4)) {   // F0 reads chunk 0 only, the dead F4 k-step 3 only: all four phases are consumed up front
+          if (o.n_kchunks == 1) {                  // F0 reads chunk 0 only: its four A_READY phases are consumed up front
             for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
             tc_fence_after();
           }
@@ -286,17 +279,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             if (lane == 0) HM_TRACE(0, 2, op, g);
             const uint32_t d = tmem_base + buf * 128;
             uint32_t fresh = 0u;                                     // the group's first MMA overwrites the buffer
+            const bool two = nwhich == 2 && stage_used(o, step, 0) && stage_used(o, step, 1);
 #pragma unroll
             for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
               for (int which = 0; which < nwhich; ++which) {
-                if (dead && op == 4 && which == 0) continue;
+                if (!stage_used(o, step, which)) continue;
                 const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
                 const uint64_t a_hi = make_desc(smem_base + kSmemA + chunk * kAChunkBytes);
                 const uint64_t a_lo = a_hi + (kALoOffset >> 4);
                 const uint64_t w_desc = make_desc(smem_base + kSmemStages + slot * kStageBytes);
                 mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
                 tc_fence_after();
-                const bool last = part == 1 && which == nwhich - 1;
+                const bool last = part == 1 && (which == nwhich - 1 || !two);
                 if (elect_one()) {
                   if (part == 0) {
 #pragma unroll
@@ -319,6 +313,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             ++gseq;
             if (lane == 0) HM_TRACE(0, 3, op, g);
           }
+          // every executed op completes one phase of all four A_READY barriers (the epilogue warps always publish all k-steps):
+          // consume the ones whose groups the plan dropped, so that the phase parity stays in step
+          for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
         }
       }
 #ifdef HM_TC_COUNTERS
@@ -347,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     const uint32_t t_addr = tmem_base + ((uint32_t)(32 * sp) << 16) + 32 * cq;
     uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 2;   // [op][thread][2 words]
     constexpr size_t kMaskStride = (size_t)kEpiWarps * 32 * 2;
-    uint32_t gseq = 0, tile_seq = 0;
+    uint32_t gseq = 0;
     int sat = 0;
 #ifdef HM_TC_COUNTERS
     long long t_pfull = 0, t_pbody = 0, t_fin = 0;       // wait-cycle counters (testing build)
@@ -361,7 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     // First of this thread's 32 consecutive columns of output half nh (within the 512-wide layer), and where they go in the
     // next A operand: chunk 4*nh + 2*hq + cq/2, k = 32*(cq & 1) + j, i.e. 16-byte units 4*(cq & 1) .. +3 of row p.
     auto col0_of = [&](int nh) { return 256 * nh + 128 * hq + 32 * cq; };
-    uint8_t* const st_row = smem + kSmemA + (uint32_t)(2 * hq + (cq >> 1)) * kAChunkBytes + (uint32_t)(p >> 3) * 1024 + (p & 7) * 128;
+    const int chunk_lo = 2 * hq + (cq >> 1);                  // this thread's output chunk within a half (add 4 * nh)
+    uint8_t* const st_row = smem + kSmemA + (uint32_t)chunk_lo * kAChunkBytes + (uint32_t)(p >> 3) * 1024 + (p & 7) * 128;
     const uint32_t u_base = 4 * (cq & 1), r7 = (uint32_t)p & 7u;
     uint32_t sat2 = 0;
     // split 8 consecutive values (one 16-byte unit u = 0..3 of this thread's 32 columns) and store the hi and lo units
@@ -379,9 +377,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     // while the tensor core works on the last op of the current one, and the lines its x0 values sit in are pulled into L2, so that
     // only L2 hits remain on the critical path at the tile start (a register prefetch of the values themselves does not fit next
     // to the 64 accumulators).
-    auto row_of = [&](int64_t unit) -> int64_t {               // global row of this thread's point (clamped for padding rows)
-      const int64_t g = (2 * unit + rank) * HM_TC_TILE_M + p;  // the odd CTA of the last pair may get an all-padding tile
-      return g < n_rows ? g : n_rows - 1;
+    auto tile_of = [&](int64_t unit) -> int64_t {             // tile index of this CTA in `unit`, -1 = padding
+      const int64_t t = 2 * unit + rank;                      // the odd CTA of the last pair may get an all-padding tile
+      if (t >= n_tiles) return -1;
+      return kRedo ? (int64_t)__ldg(P.redo + 4 + t) : t;
+    };
+    auto row_of = [&](int64_t tile) -> int64_t {              // global row of this thread's point (clamped for padding rows)
+      const int64_t g = tile * HM_TC_TILE_M + p;
+      return (tile >= 0 && g < n_rows) ? g : n_rows - 1;
     };
     auto lat_ptr_of = [&](int64_t lr, int32_t li) -> const float* {   // the 32 latent values are contiguous in both input modes
       return P.rows ? P.rows + lr * HM_IN : P.latents + (size_t)li * HM_LATENT;
@@ -392,11 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       return __ldg(P.xyz + lr * 3 + c);
     };
     auto latent_row_of = [&](int64_t lr) -> int32_t { return (!P.rows && P.row_latent) ? __ldg(P.row_latent + lr) : 0; };
-    int32_t cur_li = (unit0 < n_units) ? latent_row_of(row_of(unit0)) : 0, nxt_li = 0;
-    for (int64_t unit = unit0; unit < n_units; unit += unit_stride, ++tile_seq) {
-      const int64_t grow = (2 * unit + rank) * HM_TC_TILE_M + p;
-      const bool ok = grow < n_rows;
-      const float* const lat_ptr = lat_ptr_of(ok ? grow : n_rows - 1, cur_li);
+    int32_t cur_li = (unit0 < n_units) ? latent_row_of(row_of(tile_of(unit0))) : 0, nxt_li = 0;
+    for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
+      const int64_t tile = tile_of(unit);
+      const int64_t grow = (tile < 0 ? 0 : tile) * HM_TC_TILE_M + p;
+      const bool ok = tile >= 0 && grow < n_rows;
+      const int64_t lr = ok ? grow : n_rows - 1;
+      const float* const lat_ptr = lat_ptr_of(lr, cur_li);
       // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group g8 writes k in [8*g8, +8)
       {
         const float s0 = P.plan.ops[0].in_scale;
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           for (int i = 0; i < 8; ++i) xin[i] = __ldg(lat_ptr + 8 * g8 + i);
         } else if (g8 == 4) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) xin[c] = xyz_of(ok ? grow : n_rows - 1, c);
+          for (int c = 0; c < 3; ++c) xin[c] = xyz_of(lr, c);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) store_pair(smem, 0, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat);
@@ -420,27 +425,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       float2 acc[2][16];
       uint32_t m0 = 0u, m1 = 0u;             // ReLU bits of the current op: output half 0 / half 1, bit j = column col0 + j
       float dot = 0.f;
-      bool dead = false;                     // every lin3 output of this tile pair is 0: zero-operand shortcut (see issued_groups)
+      bool viol = false;                     // a forward op found a live unit where the sparse plan assumes zeros
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
 #pragma unroll 1
       for (int op = 0; op < kOps; ++op) {
-        if (kJac && dead && op >= 12) break;             // B3..B0 are dropped: their operand is exactly zero
         const hm_tc_op& o = P.plan.ops[op];
+        const uint32_t gm = o.group_mask;
+        if (gm == 0u) continue;                          // dropped by the plan (its A operand is exactly zero)
         const float unscale = o.out_unscale;
         const float s_next = (op + 1 < kOps) ? P.plan.ops[op + 1].in_scale : 1.f;
         const float k_mul = unscale * s_next;
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns (32 TMEM columns), one group per step
         const bool wide = (o.n_kchunks != 1);
-        const bool last_op = kJac ? (op == (dead ? 11 : kOps - 1)) : (op == kOps - 1);
-        if (last_op && unit + unit_stride < n_units) {      // next tile: latent-table row now, x0 lines into L2
-          const int64_t nr = row_of(unit + unit_stride);
+        const bool fwd_op = op < 8;
+        if (op == last_op && unit + unit_stride < n_units) {      // next tile: latent-table row now, x0 lines into L2
+          const int64_t nr = row_of(tile_of(unit + unit_stride));
           nxt_li = latent_row_of(nr);
           if (!P.rows && P.grid_n == 0 && g8 == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.xyz + nr * 3));
           if (P.rows && g8 <= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rows + nr * HM_IN + 8 * g8));
         }
+        // which of this thread's two column blocks the epilogue has to produce (all of them for a forward op: its ReLU bits are the
+        // check of the plan's assumptions; for a backward op only the columns somebody reads)
+        const uint32_t need = o.need_out;
+        const bool need0 = fwd_op || ((need >> chunk_lo) & 1u), need1 = fwd_op || ((need >> (4 + chunk_lo)) & 1u);
+        const bool emit0 = (need >> chunk_lo) & 1u, emit1 = (need >> (4 + chunk_lo)) & 1u;
         m0 = m1 = 0u;
-        if (kJac && op >= 8 && op < 15 && !(dead && op == 11)) {
+        if (kJac && op >= 8 && op < 15 && !o.is_last) {
           const uint2 mw = *reinterpret_cast<const uint2*>(my_masks + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
           m0 = mw.x; m1 = mw.y;
         }
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_PART_EMPTY + buf));
           };
-          if (narrow && cq != 0) {             // B0's 64 output columns occupy TMEM columns 0..31 only
+          if ((narrow && cq != 0) || !(nh ? need1 : need0)) {      // B0's 64 output columns occupy TMEM columns 0..31 only; unread columns are skipped
             release();
           } else {
             float v[32];
@@ -493,6 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #endif
           if (e_w == 0 && lane == 0) HM_TRACE(1 + rank, 13, opx, nh);
           const int col0 = col0_of(nh);
+          const bool emit = nh ? emit1 : emit0;                 // does the next op multiply this thread's chunk?
+          const bool may_live = (o.verify_alive >> (4 * nh + chunk_lo)) & 1u;      // may this thread's chunk hold non-zeros (forward ops)?
           if (opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
             const float* bias = bias_s + col0;
@@ -510,18 +523,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 m_ |= ((y[i] > 0.f) ? 1u : 0u) << (8 * u + i);
                 r[i] = fmaxf(y[i], 0.f);
               }
-              emit_unit(nh, u, r);
+              if (emit) emit_unit(nh, u, r);
             }
             if (nh == 1 && opx == 3 && hq == 1 && cq >= 2) {
               // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat, deep_sdf_decoder.py:87-88).
               // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the threads that
-              // own columns >= 477 rewrite those units and clear their ReLU bits.
+              // own columns >= 477 rewrite those units and clear their ReLU bits.  (Chunk 7 is always read by lin4.)
               if (cq == 3) {                           // columns 480..511 = x0[3..34]: 29 latent values + xyz, loaded as one batch
                 float xv[32];
 #pragma unroll
                 for (int j = 0; j < 29; ++j) xv[j] = __ldg(lat_ptr + 3 + j);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) xv[29 + c] = xyz_of(ok ? grow : n_rows - 1, c);
+                for (int c = 0; c < 3; ++c) xv[29 + c] = xyz_of(lr, c);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   float r[8];
@@ -544,6 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 m_ &= 0x1fffffffu;
               }
             }
+            if (!may_live && m_ != 0u) viol = true;     // the sparse plan counts on these columns being zero
             // Warps cq = 0,1 own the chunks of k-step 2*nh, warps cq = 2,3 those of k-step 2*nh + 1.  For output half 0 the
             // second pair waits for the first: the next op's first group needs k-step 0 only, and two warps per scheduler
             // deliver it in half the time four would need for both steps.
@@ -572,15 +586,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 r[2 * i] = (y.x > 0.f) ? w[2 * i] * s_next_x : 0.f;
                 r[2 * i + 1] = (y.y > 0.f) ? w[2 * i + 1] * s_next_x : 0.f;
               }
-              if (kJac) emit_unit(nh, u, r);
+              if (kJac && emit) emit_unit(nh, u, r);
             }
+            if (!may_live && m_ != 0u) viol = true;
             if (kJac) {
               publish(2 * nh + (cq >> 1));
               if (nh == 0 && cq < 2) asm volatile("bar.arrive 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
             }
-          } else if (dead && opx == 11) {
-            // ---------------- B4 of a dead tile pair: only the upper output half was issued; its skip-gradient columns 477..511 ARE
-            // the input gradient (what B3..B0 would add is exactly zero).  The tanh' factor c7 closes the chain rule.
+          } else if (o.is_last && opx < 15) {
+            // ---------------- B4 as the last op of the gradient pass (lin3 is dead in the plan: what B3..B0 would add is exactly
+            // zero): the skip-gradient columns 477..511 of d(lin4 input) ARE the input gradient.  The tanh' factor c7 closes the chain.
             if (nh == 1 && hq == 1 && cq >= 2 && ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -591,16 +606,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           } else if (opx < 15) {
             // ---------------- backward through lin_l (l = 15 - opx = 7..1): d_{l-1} = (d_l W_l) * relu'(h_{l-1})
             if (nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (emit) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float r[8];
+              for (int u = 0; u < 4; ++u) {
+                float r[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = 8 * u + i;
-                const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
-                r[i] = a * (((m_ >> j) & 1u) ? k_mul_x : 0.f);
+                for (int i = 0; i < 8; ++i) {
+                  const int j = 8 * u + i;
+                  const float a = (j & 1) ? acc[nh][j >> 1].y : acc[nh][j >> 1].x;
+                  r[i] = a * (((m_ >> j) & 1u) ? k_mul_x : 0.f);
+                }
+                emit_unit(nh, u, r);
               }
-              emit_unit(nh, u, r);
             }
             if (nh == 1 && opx == 11 && hq == 1 && cq >= 2) {
               // columns 477..511 of d(lin4 input) are the gradient w.r.t. the concatenated raw input x0 (deep_sdf_decoder.py:87-88).
@@ -627,7 +644,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         //        P(0,0) P(0,1) P(1,0) P(1,1) P(2,0) P(3,0) F(0) P(2,1) P(3,1) F(1)
         //      Output half 0 is complete two groups before the op ends and is turned into the next op's A chunks 0..3 while the
         //      tensor core still works on half 1; F(1) runs under the next op's first four groups (they read chunks 0..3 only) --
-        //      with four TMEM buffers the tensor core can be that far ahead of the promotions.
+        //      with four TMEM buffers the tensor core can be that far ahead of the promotions.  Groups the plan dropped (gm) are
+        //      skipped; a half whose opening group is among them starts from zero (0 + x = x: the same bits as an overwrite).
         if (op <= 7) {
           // stage this op's biases in shared memory (L1 is ~0 KB next to 226 KB of shared memory: a global load in the finalize
           // loop is an exposed L2 round trip)
@@ -635,18 +653,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           bias_s[e_w * 32 + lane] = __ldg(P.bias + op * HM_HIDDEN + e_w * 32 + lane);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
-        // Zero-operand shortcut (issued_groups): a dead tile pair skips the promotes of the groups that were not issued.  For the
-        // dead F4 the two surviving groups are not the ones that open their output halves, so the accumulators start at zero
-        // (0 + x = x: the same bits as an overwrite); the dead B4 keeps its upper half's opening group.
-        const uint32_t gm = kJac || op == 4 ? issued_groups(op, dead) : 0xFFu;
-        if (dead && op == 4) {
+        if (!(gm & 1u)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[0][i] = acc[1][i] = make_float2(0.f, 0.f);
+          for (int i = 0; i < 16; ++i) acc[0][i] = make_float2(0.f, 0.f);
+        }
+        if (!narrow && !(gm & 2u)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[1][i] = make_float2(0.f, 0.f);
         }
         if (gm & 1u) promote(I0, I1);
         if (narrow) {
-#pragma unroll 1
-          for (int st = 0; st < 3; ++st) promote(I0, I0);
+          if (gm & 2u) promote(I0, I0);
+          if (gm & 4u) promote(I0, I0);
+          if (gm & 8u) promote(I0, I0);
         } else {
           if (gm & 2u) promote(I1, I1);
           if (wide) {
@@ -662,24 +681,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           }
           finalize(I1, op, k_mul, unscale, s_next, m1);
           if (kJac && op < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)op * kMaskStride) = make_uint2(m0, m1);
-        }
-        if (op == 3) {
-          // ---- is any lin3 output of this tile pair alive?  (The skip-concat columns' bits were cleared above.)  One flag per
-          // CTA, exchanged through the pair's shared memories; BAR_DEAD completes when both flags of this tile are visible.
-          const bool alive = ((m0 | m1) != 0u) || !shortcut;
-          if (__any_sync(0xffffffffu, alive) && lane == 0) ctl[kCtlAlive / 4] = 1u;
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          if (e_w == 0 && lane == 0) {
-            const uint32_t par = tile_seq & 1u;
-            const uint32_t peer_ctl = mapa_rank(bars, rank ^ 1u);     // the peer CTA's control block (cluster address)
-            const uint32_t v = ctl[kCtlAlive / 4];
-            ctl[kCtlAlive / 4] = 0u;
-            ctl[kCtlFlagOwn / 4 + par] = v;
-            st_shared_cluster_u32(peer_ctl + kCtlFlagPeer + 4u * par, v);
-            mbar_arrive_release_cluster(peer_ctl + 8u * BAR_DEAD);     // orders the remote store before the peer's waiters
-            mbar_arrive(bar(BAR_DEAD));
-          }
-          dead = wait_dead_flag(tile_seq);
         }
         if (op == 7) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
@@ -708,15 +709,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           }
         }
       }
-      // ---- per-tile bookkeeping: saturation (counted per CTA tile, attributed to the latent-table row = fruit), shortcut counter
+      // ---- per-tile bookkeeping: saturation (counted per tile and thread, attributed to the latent-table row = fruit) and the
+      // sparse plan's verdict: a tile that contradicted an assumption is queued for the full plan (its outputs are rewritten there)
       if (sat | (int)((sat2 & 0xffffu) >= 0x7bffu) | (int)((sat2 >> 16) >= 0x7bffu)) {
         atomicAdd(P.flags + HM_TC_FLAG_SAT, 1);
         if (P.latent_sat && ok) P.latent_sat[cur_li] = 1;
         sat = 0;
         sat2 = 0u;
       }
-      if (dead && e_w == 0 && lane == 0 && 2 * unit + rank < n_tiles)
-        atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_DEAD_JAC : HM_TC_FLAG_DEAD_FWD)), 1ull);
+      if (!kRedo && P.plan.sparse) {
+        if (__any_sync(0xffffffffu, viol) && lane == 0) ctl[kCtlViolated / 4] = 1u;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (e_w == 0 && lane == 0 && ctl[kCtlViolated / 4]) {
+          ctl[kCtlViolated / 4] = 0u;
+          if (tile >= 0) P.redo[4 + atomicAdd(P.redo, 1)] = (int32_t)tile;
+        }
+      }
       cur_li = nxt_li;
     }
 #ifdef HM_TC_COUNTERS
@@ -737,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   }
 }
 
-// ------------------------------------------------------------------ host side: plan + weight blob
+// ------------------------------------------------------------------ host side: plans + weight blob
 float pow2_floor(float x) { return std::exp2(std::floor(std::log2(x))); }
 
 __half f2h(float x) { return __float2half_rn(x); }
@@ -754,6 +762,51 @@ void fill_tile(uint8_t* dst, int rows, float scale, int part, F&& get) {
     }
 }
 
+// the order in which the 64-wide chunks of a layer are filled with alive units: k-steps pair the chunks {0,2} {1,3} {4,6} {5,7},
+// so filling 0, 2, 1, 3, ... keeps whole k-steps (= whole accumulation groups) busy and fills output half 0 before half 1
+constexpr int kChunkFill[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+
+uint8_t groups_from_masks(const hm_tc_op& o) {
+  uint8_t gm = 0;
+  for (int g = 0; g < groups_of(o.n_kchunks, o.n_nblocks); ++g) {
+    int step, nh;
+    group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
+    const int c0 = (o.n_kchunks == 1) ? 0 : chunk_of(step, 0), c1 = (o.n_kchunks == 1) ? 0 : chunk_of(step, 1);
+    if (((o.half_mask >> nh) & 1) && (((o.chunk_mask >> c0) | (o.chunk_mask >> c1)) & 1)) gm |= (uint8_t)(1u << g);
+  }
+  return gm;
+}
+
+// amask[l] = chunks of h_l that may hold non-zeros (l = 0..7).  Fills the masks of `plan` (geometry / scales / offsets are set
+// by the caller).
+void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
+  const bool cut = amask[3] == 0;                  // lin3 dead: the gradient pass ends at lin4's skip columns
+  for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
+    hm_tc_op& o = plan.ops[op];
+    o.is_last = 0;
+    o.pad_[0] = o.pad_[1] = 0;
+    if (op < 8) {
+      o.chunk_mask = (op == 0) ? 0x01 : (op == 4) ? (uint8_t)(amask[3] | 0x80) : amask[op - 1];
+      o.half_mask = 3;
+      o.verify_alive = amask[op];
+    } else {
+      const int L = 15 - op;                        // backward through lin_L: A = d_L, output = d_{L-1} (L = 0: the input gradient)
+      const uint8_t out_cols = (L == 0) ? 0xFF : (L == 4) ? (uint8_t)(amask[3] | 0x80) : amask[L - 1];     // (B0: 35 columns, all read)
+      o.chunk_mask = (cut && L <= 3) ? 0 : amask[L];
+      o.half_mask = (L == 0) ? 1 : (uint8_t)(((out_cols & 0x0F) ? 1 : 0) | ((out_cols & 0xF0) ? 2 : 0));
+      o.verify_alive = 0xFF;
+      o.need_out = out_cols;
+      if ((cut && L == 4) || (!cut && L == 0)) o.is_last = 1;
+    }
+    o.group_mask = groups_from_masks(o);
+  }
+  for (int op = 0; op < 8; ++op) plan.ops[op].need_out = plan.ops[op + 1].chunk_mask;      // (op 7 feeds B7; ignored by forward-only passes)
+  plan.last_op_fwd = 7;
+  plan.last_op_jac = cut ? 11 : 15;
+  plan.sparse = 0;
+  for (int l = 0; l < 8; ++l) plan.sparse |= (amask[l] != 0xFF);
+}
+
 }  // namespace
 
 static int hm_tc_blob_copies() {
@@ -763,12 +816,53 @@ static int hm_tc_blob_copies() {
 }
 
 int hm_tc_init(hm_context* ctx) {
+  // ---- which hidden units were alive in the calibration pass -> unit permutation + chunk masks
+  // perm[l][new] = old index of the unit that sits at position `new` of layer l in the tensor-core engine's order
+  std::vector<int> perm[8];
+  uint8_t amask[8], afull[8];
+  const bool have_cal = ctx->unit_max.size() == (size_t)8 * HM_HIDDEN && !getenv("HM_TC_NO_SPARSE");
+  for (int l = 0; l < 8; ++l) {
+    perm[l].resize(HM_HIDDEN);
+    for (int u = 0; u < HM_HIDDEN; ++u) perm[l][u] = u;
+    amask[l] = afull[l] = 0xFF;
+    if (!have_cal) continue;
+    const float* um = ctx->unit_max.data() + (size_t)l * HM_HIDDEN;
+    if (l == 3) {                                  // lin3's columns keep their places (477 outputs + the skip-concat columns)
+      int n_alive = 0;
+      for (int u = 0; u < HM_SKIP_COL; ++u) n_alive += um[u] > 0.f;
+      amask[3] = n_alive ? 0xFF : 0x00;
+      continue;
+    }
+    std::vector<int> alive, dead;
+    for (int u = 0; u < HM_HIDDEN; ++u) (um[u] > 0.f ? alive : dead).push_back(u);
+    const int c = std::max(1, (int)(alive.size() + 63) / 64);
+    uint8_t m = 0;
+    for (int i = 0; i < c && i < 8; ++i) m |= (uint8_t)(1u << kChunkFill[i]);
+    amask[l] = m;
+    std::vector<int> order = alive;
+    order.insert(order.end(), dead.begin(), dead.end());
+    for (int k = 0; k < HM_HIDDEN; ++k) perm[l][kChunkFill[k / 64] * 64 + k % 64] = order[k];
+  }
+  // permuted weights: Wp[l][r][c] = W[l][perm_l[r]][perm_{l-1}[c]] (lin0's inputs, lin4's inputs = [h3 | x0] and lin3's outputs
+  // keep their order); lin8: columns by perm_7
+  std::vector<float> Wp[HM_LAYERS], bp[HM_LAYERS];
+  for (int l = 0; l < HM_LAYERS; ++l) {
+    const int od = ctx->out_dim[l], id = ctx->in_dim[l];
+    Wp[l].assign((size_t)od * id, 0.f);
+    bp[l].assign(od, 0.f);
+    const bool perm_rows = l < 8 && l != 3, perm_cols = l >= 1 && l != 4;
+    for (int r = 0; r < od; ++r) {
+      const int ro = perm_rows ? perm[l][r] : r;
+      bp[l][r] = ctx->h_b[l][ro];
+      for (int c = 0; c < id; ++c) Wp[l][(size_t)r * id + c] = ctx->h_W[l][(size_t)ro * id + (perm_cols ? perm[l - 1][c] : c)];
+    }
+  }
   // op list: F0..F7 (lin0..lin7), B7..B1, B0
   hm_tc_plan& plan = ctx->tc_plan;
   std::vector<uint8_t> blob;
   auto wmax = [&](int l) {
     float m = 0.f;
-    for (float v : ctx->h_W[l]) m = std::max(m, std::fabs(v));
+    for (float v : Wp[l]) m = std::max(m, std::fabs(v));
     return std::max(m, 1e-20f);
   };
   for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
@@ -778,13 +872,12 @@ int hm_tc_init(hm_context* ctx) {
     o.n_kchunks = (op == 0) ? 1 : 8;
     o.n_nblocks = (op == 15) ? 1 : 2;                // 256-column output halves (B0: one 64-column block)
     o.stage_rows = (op == 15) ? 64 : 256;
-    o.pad_ = 0;
     const float amax = std::max(ctx->act_absmax[op], 1e-20f);
     o.in_scale = pow2_floor(1024.f / amax);          // 64x headroom below the fp16 maximum
     const float w_scale = pow2_floor(8192.f / wmax(l));
     o.out_unscale = 1.f / (o.in_scale * w_scale);
     o.blob_offset = (int64_t)blob.size();
-    const std::vector<float>& W = ctx->h_W[l];
+    const std::vector<float>& W = Wp[l];
     const int in_dim = ctx->in_dim[l];
     const size_t tile_bytes = (size_t)o.stage_rows * 128;
     for (int g = 0; g < groups_of(o.n_kchunks, o.n_nblocks); ++g) {    // stages in the MMA warp's consumption order
@@ -808,6 +901,9 @@ int hm_tc_init(hm_context* ctx) {
           }
     }
   }
+  ctx->tc_plan_full = plan;
+  fill_plan_masks(ctx->tc_plan, amask);
+  fill_plan_masks(ctx->tc_plan_full, afull);
   const int copies = hm_tc_blob_copies();
   if (ctx->d_tc_blob) HM_CUDA(cudaDeviceSynchronize());      // re-calibration: no kernel on any stream may still read the old blob / biases
   if (ctx->d_tc_blob && (ctx->tc_blob_bytes != blob.size() || ctx->tc_blob_copies != copies)) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
@@ -818,44 +914,53 @@ int hm_tc_init(hm_context* ctx) {
     HM_CUDA(cudaMemcpy(ctx->d_tc_blob + (size_t)c * blob.size(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
   if (!ctx->d_tc_bias) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
+    HM_CUDA(cudaMalloc(&ctx->d_w8p, sizeof(float) * HM_HIDDEN));
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * HM_TC_FLAG_COUNT));
     HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * HM_TC_FLAG_COUNT));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   }
   std::vector<float> bias(8 * HM_HIDDEN, 0.f);
   for (int l = 0; l < 8; ++l) {
-    memcpy(bias.data() + l * HM_HIDDEN, ctx->h_b[l].data(), sizeof(float) * ctx->h_b[l].size());
+    memcpy(bias.data() + l * HM_HIDDEN, bp[l].data(), sizeof(float) * bp[l].size());
     if (l < 7)                                       // the F_l epilogue emits h_l * in_scale(F_{l+1}): fold the scale into the bias
       for (int c = 0; c < HM_HIDDEN; ++c) bias[l * HM_HIDDEN + c] *= plan.ops[l + 1].in_scale;
   }
   HM_CUDA(cudaMemcpy(ctx->d_tc_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice));
+  HM_CUDA(cudaMemcpy(ctx->d_w8p, Wp[8].data(), sizeof(float) * HM_HIDDEN, cudaMemcpyHostToDevice));
   return HM_OK;
 }
 
 void hm_tc_free(hm_context* ctx) {
   if (ctx->d_tc_blob) cudaFree(ctx->d_tc_blob);
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
+  if (ctx->d_w8p) cudaFree(ctx->d_w8p);
   if (ctx->d_tc_masks) cudaFree(ctx->d_tc_masks);
   if (ctx->d_tc_flags) cudaFree(ctx->d_tc_flags);
   if (ctx->d_tc_trace) cudaFree(ctx->d_tc_trace);
+  if (ctx->d_tc_redo) cudaFree(ctx->d_tc_redo);
   ctx->d_tc_trace = nullptr;
   ctx->d_tc_blob = nullptr;
   ctx->d_tc_bias = nullptr;
+  ctx->d_w8p = nullptr;
   ctx->d_tc_masks = nullptr;
   ctx->d_tc_flags = nullptr;
+  ctx->d_tc_redo = nullptr;
+  ctx->tc_redo_cap = 0;
 }
 
 int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st) {
   HM_CHECK(ctx->d_tc_blob, "tensor-core engine not initialised");
   TcParams P;
-  P.plan = ctx->tc_plan;
+  P.plan = ctx->sparse_plan ? ctx->tc_plan : ctx->tc_plan_full;
   P.blob = ctx->d_tc_blob;
   P.blob_bytes = (int64_t)ctx->tc_blob_bytes;
   P.blob_copies = ctx->tc_blob_copies;
   P.bias = ctx->d_tc_bias;
-  P.w8 = ctx->d_W[8];
+  P.w8 = ctx->d_w8p;
   P.b8 = ctx->d_b[8];
   P.rows = rows.d_rows;
   P.xyz = rows.d_xyz;
@@ -869,15 +974,27 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.masks = reinterpret_cast<uint32_t*>(ctx->d_tc_masks);
   P.flags = ctx->d_tc_flags;
   P.latent_sat = rows.d_latent_sat;
-  P.zero_shortcut = ctx->zero_shortcut;
   P.trace = ctx->d_tc_trace;
   P.grid_n = rows.grid_n;
   P.grid_voxel = rows.grid_voxel;
   P.grid_radius = rows.grid_radius;
+  P.redo = nullptr;
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
   const int csize = 2;                                              // the kernel is a CTA-pair kernel
   const int64_t n_units = (n_tiles + csize - 1) / csize;             // a unit = one 64-row tile per CTA of the cluster
   const int grid = (int)std::min<int64_t>(n_units, ctx->sm_count / csize) * csize;
+  const bool sparse = P.plan.sparse != 0;
+  if (sparse) {                                                     // queue of the tiles that contradict the sparse plan
+    const size_t need = (size_t)n_tiles + 8;
+    if (need > ctx->tc_redo_cap) {
+      if (ctx->d_tc_redo) { HM_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->d_tc_redo); ctx->d_tc_redo = nullptr; }
+      const size_t cap = std::max(need, (size_t)1 << 16);
+      HM_CUDA(cudaMalloc(&ctx->d_tc_redo, sizeof(int32_t) * cap));
+      ctx->tc_redo_cap = cap;
+    }
+    HM_CUDA(cudaMemsetAsync(ctx->d_tc_redo, 0, 16, st));
+    P.redo = ctx->d_tc_redo;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -890,10 +1007,16 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true>, P));
-  else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false>, P));
+  if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, false>, P));
+  else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, false>, P));
   ctx->counters.kernel_launches += 1;
+  if (sparse) {
+    // second pass: the queued tiles with the full plan (the kernel returns at once when the queue is empty)
+    P.plan = ctx->tc_plan_full;
+    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, true>, P));
+    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, true>, P));
+    ctx->counters.kernel_launches += 1;
+  }
   HM_CUDA(cudaGetLastError());
   return HM_OK;
 }
-

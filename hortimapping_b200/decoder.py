@@ -112,9 +112,10 @@ class Decoder:
         code = {"tc": _lib.HM_ENGINE_TC, "simt": _lib.HM_ENGINE_SIMT}[engine]
         check(self._L.hm_set_engine(self._h, code), "hm_set_engine")
 
-    def set_zero_shortcut(self, on: bool):
-        """Tensor-core engine: skip the MMAs whose A operand is exactly zero (dead lin3); bit-identical results either way."""
-        check(self._L.hm_set_zero_shortcut(self._h, int(bool(on))), "hm_set_zero_shortcut")
+    def set_sparse_plan(self, on: bool):
+        """Tensor-core engine: use the calibrated sparse plan (MMAs on all-zero activation chunks are dropped, checked per tile,
+        violators re-evaluated with the full plan); results are bit-identical either way."""
+        check(self._L.hm_set_sparse_plan(self._h, int(bool(on))), "hm_set_sparse_plan")
 
     def calibrate(self, rows: torch.Tensor):
         rows = _f32c(rows.reshape(-1, HM_IN), self.device)
@@ -282,8 +283,11 @@ def config_decoder(experiment_directory: str, checkpoint: str = "latest", device
             codes = codes.to(dec.device)
             clamp = float(specs.get("ClampingDistance", 0.1))
             g = torch.Generator(device="cpu").manual_seed(0)
-            n = 8192
+            n = 65536
+            # training codes with a little jitter: the optimisers move latents off the training set, and a hidden unit that only
+            # fires there would otherwise send its tiles to the full plan (correct, but slower)
             z = codes[torch.randint(0, codes.shape[0], (n,), generator=g).to(dec.device)]
+            z = z + (0.03 * torch.randn(n, HM_LATENT, generator=g)).to(dec.device)
             x = ((torch.rand(n, 3, generator=g) * 2 - 1) * 1.5 * clamp).to(dec.device)
             dec.calibrate(torch.cat([z, x], 1))
             dec.calibration = f"{codes.shape[0]} training codes of {lat_file}"

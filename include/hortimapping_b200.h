@@ -131,8 +131,8 @@ typedef struct hm_counters {
   double jacobian_ms;
   int64_t tiles_forward;      /* 64-row tiles processed by forward-only / forward+gradient launches             */
   int64_t tiles_jacobian;
-  int64_t tiles_dead_forward; /* ... of which took the exact zero-operand shortcut (all lin3 outputs of the      */
-  int64_t tiles_dead_jacobian;/*     tile pair are 0 after the ReLU)                              */
+  int64_t tiles_redone_forward;  /* ... of which contradicted the sparse plan and were re-evaluated with the full  */
+  int64_t tiles_redone_jacobian; /*     plan (hm_set_sparse_plan; 0 for the shipped models on calibrated rows)     */
 } hm_counters;
 
 const char* hm_last_error(void);
@@ -143,11 +143,13 @@ int hm_create(hm_context** out, int device, const hm_decoder_desc* dec);
 void hm_destroy(hm_context* ctx);
 int hm_set_engine(hm_context* ctx, int engine);
 int hm_get_engine(const hm_context* ctx);
-/* Tensor-core engine: the zero-operand shortcut (on by default).  When every lin3 output of a 128-row tile pair is 0 after the
- * ReLU -- true for every row of both shipped models -- the MMAs whose A operand is exactly zero are not issued.  The skipped
- * products are exact zeros, so results are bit-identical with the shortcut off; the switch exists for that test and for
- * measurements (hm_counters.tiles_dead_* count the tiles that took it). */
-int hm_set_zero_shortcut(hm_context* ctx, int on);
+/* Tensor-core engine: the sparse plan (on by default).  hm_calibrate records which hidden units were ever alive on the
+ * calibration rows; the engine orders the units so that those come first and drops every MMA whose A operand is then an
+ * all-zero 64-wide chunk of the activations (both shipped models: lin3 is dead outright, 12 .. 320 of 512 units alive elsewhere).
+ * The assumption is checked per 64-row tile from the ReLU bits; a tile that contradicts it is re-evaluated with the full plan
+ * by a second launch (hm_counters.tiles_redone_*).  Dropped products are exact zeros: results are bit-identical with the plan
+ * off; the switch exists for that test and for measurements. */
+int hm_set_sparse_plan(hm_context* ctx, int on);
 /* Choose the power-of-two fp16 operand scales of the TC engine from sample rows [n][35] (device). */
 int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
 /* With profiling enabled every decoder kernel launch is bracketed by CUDA events on its stream; hm_get_counters synchronises the

@@ -27,7 +27,7 @@ def main():
     W, b, codes = B.load_weights()
     dec = Decoder(W, b, device=0)
     g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 8192)], ((g.random((8192, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
+    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
     dec.calibrate(torch.from_numpy(cal))
     cfg = copy.deepcopy(B.WILD_CFG)
     cfg["opt"]["converge"]["max_iter"] = 2

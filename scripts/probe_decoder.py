@@ -29,7 +29,7 @@ def make_rows(codes, n=N, seed=0):
 
 def calibrated(dec, codes):
     g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 8192)], ((g.random((8192, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
+    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
     dec.calibrate(torch.from_numpy(cal))
     return dec
 
@@ -54,13 +54,13 @@ def main():
         from hortimapping_b200.decoder import Decoder
         dec = calibrated(Decoder(W, b), codes)
         for on in (True, False):
-            dec.set_zero_shortcut(on)
+            dec.set_sparse_plan(on)
             c0 = dec.counters()
             f, j = ms_of(lambda: dec._eval_rows(t, with_jac=False)), ms_of(lambda: dec._eval_rows(t, with_jac=True))
             c1 = dec.counters()
-            print(f"shortcut {'on ' if on else 'off'}: forward {f:.3f} ms ({N * 3.67104e6 / f / 1e9:.0f} TFLOP/s algorithmic)  forward+gradient {j:.3f} ms "
-                  f"({N * 7.34208e6 / j / 1e9:.0f} TFLOP/s)  dead tiles {c1['tiles_dead_forward'] - c0['tiles_dead_forward']}/{c1['tiles_forward'] - c0['tiles_forward']} fwd, "
-                  f"{c1['tiles_dead_jacobian'] - c0['tiles_dead_jacobian']}/{c1['tiles_jacobian'] - c0['tiles_jacobian']} jac")
+            print(f"sparse plan {'on ' if on else 'off'}: forward {f:.3f} ms ({N * 3.67104e6 / f / 1e9:.0f} TFLOP/s algorithmic)  forward+gradient {j:.3f} ms "
+                  f"({N * 7.34208e6 / j / 1e9:.0f} TFLOP/s)  re-evaluated tiles {c1['tiles_redone_forward'] - c0['tiles_redone_forward']}/{c1['tiles_forward'] - c0['tiles_forward']} fwd, "
+                  f"{c1['tiles_redone_jacobian'] - c0['tiles_redone_jacobian']}/{c1['tiles_jacobian'] - c0['tiles_jacobian']} jac")
         return
     dec = calibrated(_testing.testing_decoder(W, b), codes)
     L = _testing.lib()

@@ -13,8 +13,8 @@ def pepper_decoder():
         W, b, codes = pepper_weights()
         dec = Decoder(W, b)
         g = np.random.default_rng(0)
-        z = codes[g.integers(0, codes.shape[0], 8192)]
-        x = ((g.random((8192, 3)) * 2 - 1) * 0.15).astype(np.float32)
+        z = codes[g.integers(0, codes.shape[0], 65536)]
+        x = ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)
         dec.calibrate(torch.from_numpy(np.concatenate([z, x], 1)))
         _cache["pepper"] = dec
     return _cache["pepper"]

@@ -171,7 +171,22 @@ def test_shape_opt_deepsdf_vs_reference():
     assert rel(H[0], c["shape_H"][0]) < 1e-4
     assert rel(b[0], c["shape_b"][0]) < 1e-4
     assert rel(dx[0], c["shape_dx"][0]) < 1e-3
-    # 30 iterations: latent-only LM is well conditioned -> element-wise agreement with the fp64 reference
+    # the convergent phase (|dx| falls from 8e-2 to 1e-4 in ~6 iterations) is held to north_star's 1e-4 element-wise, both engines,
+    # against the fp64 oracle run from the same start
+    cfg5 = zero_eps(cfg_of(c), 5)
+    l64 = c["init_latent"].astype(np.float64).copy()
+    O.shape_opt_deepsdf(oracle_decoder(np.float64), cfg5, l64, c["init_T_ow"].astype(np.float64), c["points_w"])
+    for engine in ("tc", "simt"):
+        opt5, dec5 = make_opt(cfg5, engine)
+        try:
+            l5 = torch.from_numpy(c["init_latent"].copy()).cuda().reshape(1, 32)
+            opt5.shape_opt_deepsdf_batch(l5, T.clone(), [c["points_w"]], max_iter=5)
+        finally:
+            dec5.set_engine("tc")
+        assert rel(l5[0].cpu().numpy(), l64) < 1e-4, engine
+    # 30 iterations: past convergence the loop keeps moving by ~1e-4 per iteration along flat directions (|b| at its fp32 cancellation
+    # floor, single rows crossing ReLU kinks) and any two correct runs drift ~1e-3 apart (scripts/diag_parity.py: the reference's
+    # fp32 vs fp64 runs, numpy fp32, both device engines) -> held to the reference's own fp32-vs-fp64 distance
     cfg30 = zero_eps(cfg_of(c), 30)
     opt30, _ = make_opt(cfg30)
     latent = torch.from_numpy(c["init_latent"].copy()).cuda()
