@@ -55,7 +55,7 @@ class Counters(C.Structure):
 _lib = None
 
 # every symbol include/hortimapping_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_sparse_plan", "hm_calibrate",
+EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_sparse_plan", "hm_plan_info", "hm_calibrate",
            "hm_get_counters", "hm_saturation_count", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
            "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays",
@@ -84,6 +84,7 @@ def bind(L: C.CDLL) -> C.CDLL:
     L.hm_set_engine.argtypes = [C.c_void_p, C.c_int]
     L.hm_get_engine.argtypes = [C.c_void_p]
     L.hm_set_sparse_plan.argtypes = [C.c_void_p, C.c_int]
+    L.hm_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.hm_calibrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hm_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.hm_profile_enable.argtypes = [C.c_void_p, C.c_int]

@@ -155,6 +155,12 @@ extern "C" int hm_set_sparse_plan(hm_context* ctx, int on) {
   return HM_OK;
 }
 
+extern "C" int hm_plan_info(const hm_context* ctx, double* h_out) {
+  HM_CHECK(ctx && h_out, "hm_plan_info: null argument");
+  hm_tc_plan_info(ctx, h_out);
+  return HM_OK;
+}
+
 extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
   HM_CHECK(ctx && out, "hm_get_counters: null argument");
   HM_CUDA(cudaSetDevice(ctx->device));

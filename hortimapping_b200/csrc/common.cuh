@@ -98,7 +98,7 @@ struct hm_context {
   hm_tc_plan tc_plan_full;         // every mask full: the reference evaluation, used for the tiles that fail the sparse plan's checks
   int32_t* d_tc_redo = nullptr;    // [0] = number of queued tiles, [4 ..] = their indices (grow-only)
   size_t tc_redo_cap = 0;
-  float* d_w8p = nullptr;          // lin8 weight in the permuted unit order of the tensor-core engine
+  float h_w8p[HM_HIDDEN] = {};     // lin8 weight in the permuted unit order of the tensor-core engine (travels as a kernel parameter)
   float act_absmax[HM_TC_NOPS_ALL] = {};   // calibration result: max |A operand| per op
   std::vector<float> unit_max;             // calibration result: [8][512] largest activation of every hidden unit (0 = never alive)
   float* d_tc_bias = nullptr;      // [8][512] biases of lin0..7 (lin3 padded with 0)
@@ -198,6 +198,7 @@ int hm_simt_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_
 int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st);
 int hm_tc_init(hm_context* ctx);          // build weight blob + plan from ctx->h_W and act_absmax
 void hm_tc_free(hm_context* ctx);
+void hm_tc_plan_info(const hm_context* ctx, double* out /* [12], hm_plan_info */);
 int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, cudaStream_t st);
 
 // ---- optimiser (optimizer.cu) ----

@@ -71,8 +71,7 @@ struct TcParams {
   int64_t blob_bytes;         // size of one copy of the weight blob
   int32_t blob_copies;        // copies laid out back to back (CTAs spread over them)
   const float* bias;          // [8][512]
-  const float* w8;            // [512]
-  const float* b8;            // [1]
+  float b8;                   // lin8 bias
   const float* rows;          // [n][35] or null
   const float* xyz;           // [n][3]
   const float* latents;       // [L][32]
@@ -89,7 +88,11 @@ struct TcParams {
   int32_t grid_n;             // > 0: xyz of row i = voxel grid point i (fused mesher grid, hm_rows)
   float grid_voxel, grid_radius;
   int32_t* redo;              // [0] = number of queued tiles, [4 ..] = tile indices: appended by the sparse pass, read by the redo pass
+  // lin8 weight (permuted unit order).  Every lane of an epilogue warp reads the SAME columns, so the kernel-parameter constant
+  // bank serves it at register speed; a global load in the finalize loop is an exposed L2 round trip (the L1 is ~0 KB here).
+  alignas(16) float w8[HM_HIDDEN];
 };
+static_assert(sizeof(TcParams) <= 4096, "kernel parameters exceed the 4 KB every driver accepts");
 
 // k-chunk order of an 8-chunk op: k-step s multiplies chunks {0,2}, {1,3}, {4,6}, {5,7}.  Steps 0,1 read the chunks that the
 // previous op's output half 0 becomes (0..3), steps 2,3 those of its half 1 (4..7).
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             if (kJac && nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(w8 + 8 * u)), w1 = __ldg(reinterpret_cast<const float4*>(w8 + 8 * u + 4));
+              const float4 w0 = *reinterpret_cast<const float4*>(w8 + 8 * u), w1 = *reinterpret_cast<const float4*>(w8 + 8 * u + 4);
               const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
               float r[8];
 #pragma unroll
@@ -682,18 +685,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           finalize(I1, op, k_mul, unscale, s_next, m1);
           if (kJac && op < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)op * kMaskStride) = make_uint2(m0, m1);
         }
-        if (op == 7) {
+        // ---- lin8 + tanh (deep_sdf_decoder.py:107-108): every thread sums the 8 column-group partials of its point.  A forward-only
+        //      pass does it at the end of F7 (= the end of the tile).  With the gradient requested it is DEFERRED to the end of B7's
+        //      epilogue: nothing needs the SDF or tanh' before the last gradient op, and here it would sit between F7's last finalize
+        //      and B7's first promotion, i.e. on the critical path of the op chain; there it runs while the tensor core works on B6.
+        if ((!kJac && op == 7) || (kJac && op == 8)) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
           dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          const float b8 = __ldg(P.b8);
           const float4 d0 = *reinterpret_cast<const float4*>(dot_scratch + p * 8), d1 = *reinterpret_cast<const float4*>(dot_scratch + p * 8 + 4);
-          f_out = tanhf((((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w))) + b8);
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          f_out = tanhf((((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w))) + P.b8);
+          // (no barrier behind the reads: the next writer of this memory is the bias staging of the next tile's F0, which starts
+          // with a barrier of its own)
           dot = 0.f;
           c7 = 1.f - f_out * f_out;                                             // tanh' (deep_sdf_decoder.py:107-108)
           if (g8 == 0 && ok) P.sdf[P.out_index ? (int64_t)__ldg(P.out_index + grow) : grow] = f_out;
-        } else if (op == 15) {
+        }
+        if (op == 15) {
           // ---------------- B0: g = c7 * (d0 W0 + the parked skip gradient) (35 valid of 64 columns: TMEM columns 0..31 of lanes
           //                  0..63 hold columns 0..31, of lanes 64..127 columns 32..63)
           if (cq == 0 && ok) {
@@ -914,7 +922,6 @@ int hm_tc_init(hm_context* ctx) {
     HM_CUDA(cudaMemcpy(ctx->d_tc_blob + (size_t)c * blob.size(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
   if (!ctx->d_tc_bias) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
-    HM_CUDA(cudaMalloc(&ctx->d_w8p, sizeof(float) * HM_HIDDEN));
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * HM_TC_FLAG_COUNT));
     HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * HM_TC_FLAG_COUNT));
@@ -930,14 +937,41 @@ int hm_tc_init(hm_context* ctx) {
       for (int c = 0; c < HM_HIDDEN; ++c) bias[l * HM_HIDDEN + c] *= plan.ops[l + 1].in_scale;
   }
   HM_CUDA(cudaMemcpy(ctx->d_tc_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice));
-  HM_CUDA(cudaMemcpy(ctx->d_w8p, Wp[8].data(), sizeof(float) * HM_HIDDEN, cudaMemcpyHostToDevice));
+  memcpy(ctx->h_w8p, Wp[8].data(), sizeof(float) * HM_HIDDEN);
   return HM_OK;
+}
+
+// Tensor-core FLOP issued per row by a plan: every issued stage pair is 4 (A_hi x W_lo) + 8 (A_lo x W_hi, A_hi x W_hi) MMAs of
+// M = 128 rows (one tile pair) x N = stage_rows x K = 16.
+static double plan_flop_per_row(const hm_tc_plan& plan, bool jac) {
+  double f = 0;
+  const int n_ops = jac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
+  for (int op = 0; op < n_ops; ++op) {
+    const hm_tc_op& o = plan.ops[op];
+    for (int g = 0; g < groups_of(o.n_kchunks, o.n_nblocks); ++g) {
+      if (!((o.group_mask >> g) & 1u)) continue;
+      int step, nh;
+      group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
+      for (int which = 0; which < (o.n_kchunks == 1 ? 1 : 2); ++which) {
+        const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+        if ((o.chunk_mask >> chunk) & 1u) f += 12.0 * 2.0 * o.stage_rows * 16;
+      }
+    }
+  }
+  return f;
+}
+
+void hm_tc_plan_info(const hm_context* ctx, double* out) {
+  out[0] = plan_flop_per_row(ctx->tc_plan, false);
+  out[1] = plan_flop_per_row(ctx->tc_plan, true);
+  out[2] = plan_flop_per_row(ctx->tc_plan_full, false);
+  out[3] = plan_flop_per_row(ctx->tc_plan_full, true);
+  for (int l = 0; l < 8; ++l) out[4 + l] = __builtin_popcount(ctx->tc_plan.ops[l].verify_alive);
 }
 
 void hm_tc_free(hm_context* ctx) {
   if (ctx->d_tc_blob) cudaFree(ctx->d_tc_blob);
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
-  if (ctx->d_w8p) cudaFree(ctx->d_w8p);
   if (ctx->d_tc_masks) cudaFree(ctx->d_tc_masks);
   if (ctx->d_tc_flags) cudaFree(ctx->d_tc_flags);
   if (ctx->d_tc_trace) cudaFree(ctx->d_tc_trace);
@@ -945,7 +979,6 @@ void hm_tc_free(hm_context* ctx) {
   ctx->d_tc_trace = nullptr;
   ctx->d_tc_blob = nullptr;
   ctx->d_tc_bias = nullptr;
-  ctx->d_w8p = nullptr;
   ctx->d_tc_masks = nullptr;
   ctx->d_tc_flags = nullptr;
   ctx->d_tc_redo = nullptr;
@@ -960,8 +993,8 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.blob_bytes = (int64_t)ctx->tc_blob_bytes;
   P.blob_copies = ctx->tc_blob_copies;
   P.bias = ctx->d_tc_bias;
-  P.w8 = ctx->d_w8p;
-  P.b8 = ctx->d_b[8];
+  memcpy(P.w8, ctx->h_w8p, sizeof(P.w8));
+  P.b8 = ctx->h_b[8][0];
   P.rows = rows.d_rows;
   P.xyz = rows.d_xyz;
   P.latents = rows.d_latents;

@@ -150,6 +150,12 @@ int hm_get_engine(const hm_context* ctx);
  * by a second launch (hm_counters.tiles_redone_*).  Dropped products are exact zeros: results are bit-identical with the plan
  * off; the switch exists for that test and for measurements. */
 int hm_set_sparse_plan(hm_context* ctx, int on);
+/* What the tensor-core engine ISSUES per decoder row under the current calibration (measurement aid: the roofline's algorithmic
+ * FLOPs are the reference's dense count, deep_sdf_decoder.py:75-110; this is the work actually sent to the tensor cores):
+ * h_out[0] / [1] = tensor-core FLOP per row of a forward / forward + gradient evaluation with the sparse plan, [2] / [3] = the
+ * same with the full plan (three fp16 products per fp32 product, padding included), [4 .. 11] = 64-wide chunks of h_0 .. h_7 the
+ * sparse plan treats as possibly non-zero (8 = no assumption).  h_out has 12 entries. */
+int hm_plan_info(const hm_context* ctx, double* h_out);
 /* Choose the power-of-two fp16 operand scales of the TC engine from sample rows [n][35] (device). */
 int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
 /* With profiling enabled every decoder kernel launch is bracketed by CUDA events on its stream; hm_get_counters synchronises the

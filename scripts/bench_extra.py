@@ -46,8 +46,8 @@ def main():
     W, b, codes = B.load_weights()
     dec = Decoder(W, b, device=0)
     g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
-    dec.calibrate(torch.from_numpy(cal))
+    from hortimapping_b200.decoder import calibration_rows
+    dec.calibrate(calibration_rows(codes, 0.15))
     lat = torch.from_numpy(codes.mean(0).astype(np.float32)).cuda()
     n = 128
     if "grid" in which or "iso" in which:

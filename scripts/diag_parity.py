@@ -33,9 +33,9 @@ def main():
     init = codes.mean(0).astype(np.float32)
     dec = Decoder(W, b, device=0)
     g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
-    dec.calibrate(torch.from_numpy(cal))
-    fr = synth.make_fruit(B.product_sdf_jac(dec), codes, 0, int(os.environ.get("DIAG_FRUIT", "0")), n_pts=B.N_PTS, with_rays=False)
+    from hortimapping_b200.decoder import calibration_rows
+    dec.calibrate(calibration_rows(codes, 0.15))
+    fr = synth.make_fruit(B.product_sdf_jac(dec), codes, int(os.environ.get("DIAG_SEED", "7")), int(os.environ.get("DIAG_FRUIT", "0")), n_pts=B.N_PTS, with_rays=False)
     pts = fr.points_w
     T_ow = np.linalg.inv(fr.T_wo_gt.astype(np.float64)).astype(np.float32)
     mm, _ = B._torch_mm()

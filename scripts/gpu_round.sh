@@ -22,19 +22,17 @@ if has full; then
       python scripts/ncu_target.py 2>&1 | tail -3 ) > gpurun_out/ncu_full.log; tail -2 gpurun_out/ncu_full.log
   python scripts/summarise_ncu_kernels.py /tmp/prof_all.ncu-rep gpurun_out/ncu_kernels.txt > /dev/null 2>&1
   ncu -i /tmp/prof_all.ncu-rep --page raw --csv > gpurun_out/ncu_kernels_raw.csv 2>/dev/null
-  for k in "tc_decoder_kernel<true>:jac" "tc_decoder_kernel<false>:fwd" "solve_kernel:solve" "normal_eq_kernel:normal_eq"; do
-    pat=${k%%:*}; tag=${k##*:}
-    ncu -i /tmp/prof_all.ncu-rep --page source --csv -k "regex:${pat%%<*}" > /tmp/src_$tag.csv 2>/dev/null
-  done
   # the two decoder instantiations share a name prefix: split by launch id (forward-only launches carry <(bool)0>)
   python - <<'PY'
-import csv, subprocess, sys, os
+import csv, subprocess, sys, os, re
 rows = list(csv.reader(subprocess.run(["ncu", "-i", "/tmp/prof_all.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 hdr = rows[0]; iid, iname = hdr.index("ID"), hdr.index("Kernel Name")
 pick = {}
 for r in rows[2:]:
     n = r[iname]
-    key = "jac" if "tc_decoder_kernel<1>" in n or "tc_decoder_kernel<(bool)1>" in n else "fwd" if "tc_decoder_kernel" in n else "solve" if "solve_kernel" in n else "normal_eq" if "normal_eq" in n else None
+    # tc_decoder_kernel<kJac, kRedo>: the redo instantiations (second template argument 1) exit at once on these inputs
+    key = ("jac" if re.search(r"tc_decoder_kernel<(\(bool\))?1, (\(bool\))?0>", n) else "fwd" if re.search(r"tc_decoder_kernel<(\(bool\))?0, (\(bool\))?0>", n)
+           else "solve" if "solve_kernel" in n else "normal_eq" if "normal_eq" in n else None)
     if key and key not in pick: pick[key] = r[iid]
 for key, lid in pick.items():
     src = subprocess.run(["ncu", "-i", "/tmp/prof_all.ncu-rep", "--page", "source", "--csv", "--launch-skip", lid, "--launch-count", "1"], capture_output=True, text=True).stdout
@@ -46,11 +44,12 @@ PY
 fi
 if has memcheck; then
   ( timeout -k 5 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_optimizer.py -m gpu -q -x \
-      -k "shortcut or ragged or replay or batch_equals or invalid_submap or degenerate" 2>&1 | tail -15 ) > gpurun_out/sanitizer_memcheck.log; tail -4 gpurun_out/sanitizer_memcheck.log
+      -k "sparse_plan or contradict or ragged or replay or batch_equals or invalid_submap or degenerate" 2>&1 | tail -15 ) > gpurun_out/sanitizer_memcheck.log; tail -4 gpurun_out/sanitizer_memcheck.log
 fi
 if has racecheck; then
   ( timeout -k 5 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py -m gpu -q -x \
-      -k "ragged and (129 or 1000)" 2>&1 | tail -150 ) > gpurun_out/sanitizer_racecheck.log; tail -4 gpurun_out/sanitizer_racecheck.log
+      -k "ragged and (129 or 1000)" > /tmp/racecheck_full.log 2>&1 )
+  python scripts/summarise_racecheck.py /tmp/racecheck_full.log > gpurun_out/sanitizer_racecheck.log 2>&1; tail -12 gpurun_out/sanitizer_racecheck.log
 fi
 if has extra; then
   ( timeout -k 5 600 python scripts/bench_extra.py grid iso nn render_data 2>&1 | grep "^{" ) > gpurun_out/extra.log; cat gpurun_out/extra.log | cut -c1-300

@@ -27,8 +27,8 @@ def main():
     W, b, codes = B.load_weights()
     dec = Decoder(W, b, device=0)
     g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
-    dec.calibrate(torch.from_numpy(cal))
+    from hortimapping_b200.decoder import calibration_rows
+    dec.calibrate(calibration_rows(codes, 0.15))
     cfg = copy.deepcopy(B.WILD_CFG)
     cfg["opt"]["converge"]["max_iter"] = 2
     opt = Optimizer(cfg, dec, None, None)

@@ -28,9 +28,8 @@ def make_rows(codes, n=N, seed=0):
 
 
 def calibrated(dec, codes):
-    g = np.random.default_rng(0)
-    cal = np.concatenate([codes[g.integers(0, codes.shape[0], 65536)], ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)], 1)
-    dec.calibrate(torch.from_numpy(cal))
+    from hortimapping_b200.decoder import calibration_rows
+    dec.calibrate(calibration_rows(codes, 0.15))
     return dec
 
 

@@ -12,10 +12,8 @@ def pepper_decoder():
         from hortimapping_b200.decoder import Decoder
         W, b, codes = pepper_weights()
         dec = Decoder(W, b)
-        g = np.random.default_rng(0)
-        z = codes[g.integers(0, codes.shape[0], 65536)]
-        x = ((g.random((65536, 3)) * 2 - 1) * 0.15).astype(np.float32)
-        dec.calibrate(torch.from_numpy(np.concatenate([z, x], 1)))
+        from hortimapping_b200.decoder import calibration_rows
+        dec.calibrate(calibration_rows(codes, 0.15))          # the recipe config_decoder uses
         _cache["pepper"] = dec
     return _cache["pepper"]
 
