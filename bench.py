@@ -458,17 +458,20 @@ def main():
         return float(ms.item()), {k: c1[k] - c0[k] for k in c1}, clocks, res
 
     def roofline_of(dc, total_ms, kernel):
-        flop = dc["rows_forward"] * FLOP_PER_FWD_ROW + dc["rows_jacobian"] * FLOP_PER_JAC_ROW
+        # (a gradient-only row costs the backward half: the same MAC count as a forward row)
+        flop = (dc["rows_forward"] + dc["rows_backward"]) * FLOP_PER_FWD_ROW + dc["rows_jacobian"] * FLOP_PER_JAC_ROW
         n_launch, dec_ms = dc["decoder_launches"], dc["decoder_ms"]
         achieved = flop / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else None
-        tiles = dc["tiles_forward"] + dc["tiles_jacobian"]
-        redone = dc["tiles_redone_forward"] + dc["tiles_redone_jacobian"]
+        tiles = dc["tiles_forward"] + dc["tiles_jacobian"] + dc["tiles_backward"]
+        redone = dc["tiles_redone_forward"] + dc["tiles_redone_jacobian"] + dc["tiles_redone_backward"]
         r = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
              "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-             "rows_forward": dc["rows_forward"], "rows_jacobian": dc["rows_jacobian"], "rows_counted": "exact (device-side counters)",
+             "rows_forward": dc["rows_forward"], "rows_jacobian": dc["rows_jacobian"], "rows_gradient_only": dc["rows_backward"],
+             "rows_counted": "exact (device-side counters)",
              "algorithmic_flop_per_launch": flop / max(n_launch, 1), "launches": n_launch, "avg_launch_ms": dec_ms / max(n_launch, 1),
              "forward_launches": dc["forward_launches"], "forward_ms": dc["forward_ms"],
              "jacobian_launches": dc["jacobian_launches"], "jacobian_ms": dc["jacobian_ms"],
+             "gradient_only_launches": dc["backward_launches"], "gradient_only_ms": dc["backward_ms"],
              "tiles": tiles, "tiles_re_evaluated_with_full_plan": redone,
              "kernel_share_of_step": dec_ms / total_ms if total_ms > 0 else None}
         # `achieved` counts the reference's dense FLOPs (what the reference computes per row).  The engine issues something else:
@@ -477,12 +480,15 @@ def main():
         pi = dec.plan_info()
         ipr = pi["issued_flop_per_row"]
         issued = (dc["rows_forward"] * ipr["sparse_forward"] + dc["rows_jacobian"] * ipr["sparse_jacobian"]
-                  + 64 * (dc["tiles_redone_forward"] * ipr["full_forward"] + dc["tiles_redone_jacobian"] * ipr["full_jacobian"]))
+                  + dc["rows_backward"] * (ipr["sparse_jacobian"] - ipr["sparse_forward"])
+                  + 64 * (dc["tiles_redone_forward"] * ipr["full_forward"] + dc["tiles_redone_jacobian"] * ipr["full_jacobian"]
+                          + dc["tiles_redone_backward"] * (ipr["full_jacobian"] - ipr["full_forward"])))
         r["issued"] = {"what": "fp16 tensor-core FLOP actually issued (3 products per fp32 product, sparse plan, padding, re-evaluated tiles)",
                        "tflops": issued / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else None,
                        "frac_of_peak": issued / (dec_ms * 1e-3) / 1e12 / peak if dec_ms > 0 else None,
                        "flop_per_row": ipr, "alive_chunks_per_layer_of_8": pi["alive_chunks_per_layer"],
-                       "dense_plan_would_issue_x": (dc["rows_forward"] * ipr["full_forward"] + dc["rows_jacobian"] * ipr["full_jacobian"]) / issued if issued else None}
+                       "dense_plan_would_issue_x": (dc["rows_forward"] * ipr["full_forward"] + dc["rows_jacobian"] * ipr["full_jacobian"]
+                                                    + dc["rows_backward"] * (ipr["full_jacobian"] - ipr["full_forward"])) / issued if issued else None}
         tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tfile):       # one ncu --set full capture of this kernel (static file, named so it can go stale visibly)
             tj = json.load(open(tfile))
@@ -625,8 +631,10 @@ def main():
                                    "20 % leaf-occluded background rays"},
             "e2e": {"value": j_e2e, "unit": "fruits/s", "h2d_bytes_per_step": j_h2d, "d2h_bytes_per_step": j_d2h, "steps": 1},
             "host_equals_device": bool(torch.equal(wj.to(dev), jlat)),
-            "roofline": roofline_of(jdc, j_ms, "tc_decoder_kernel<false> (in-sphere ray samples, forward) + tc_decoder_kernel<true> (recon points + in-band samples)"),
-            "rows_per_fruit_iteration": {"forward": jdc["rows_forward"] / (N_JOINT * n_it_total), "forward_plus_gradient": jdc["rows_jacobian"] / (N_JOINT * n_it_total)},
+            "roofline": roofline_of(jdc, j_ms, "tc_decoder_kernel<0> (in-sphere ray samples: forward, ReLU bits kept) + <1> (observed points: forward + gradient) + "
+                                                  "<2> (in-band samples: gradient only, from the kept bits)"),
+            "rows_per_fruit_iteration": {"forward": jdc["rows_forward"] / (N_JOINT * n_it_total), "forward_plus_gradient": jdc["rows_jacobian"] / (N_JOINT * n_it_total),
+                                         "gradient_only": jdc["rows_backward"] / (N_JOINT * n_it_total)},
             "clocks": jclocks, "gpu_launches": jdc["kernel_launches"], "status_bits_seen": sorted({hex(int(x)) for x in jst.cpu().tolist()})}
         f0 = fruits[0]
         joint_io = {"j_init_lat": f0.init_latent, "j_init_T": f0.init_T_ow, "j_points_w": f0.points_w, "rd": f0.render_data}
@@ -639,7 +647,7 @@ def main():
         gH, gb, gdx = (t.cpu().numpy()[0] for t in opt.last_system(1))
         c_b = dec.counters()
         g_it0 = {"H": gH, "b": gb, "dx": gdx, "latent": l1[0].cpu().numpy(), "T_ow": T1[0].cpu().numpy(),
-                 "rows_fwd": c_b["rows_forward"] - c_a["rows_forward"], "rows_jac": c_b["rows_jacobian"] - c_a["rows_jacobian"]}
+                 "rows_fwd": c_b["rows_forward"] - c_a["rows_forward"], "rows_jac": (c_b["rows_jacobian"] - c_a["rows_jacobian"]) + (c_b["rows_backward"] - c_a["rows_backward"])}
         # the same step with the library's fp32 CUDA-core decoder (HM_ENGINE_SIMT, an independent device implementation of the MLP):
         # separates the loss / normal-equation arithmetic from the rounding of the tensor-core decoder
         dec.set_engine("simt")

@@ -49,13 +49,15 @@ class Counters(C.Structure):
                 ("iterations", C.c_int64), ("decoder_launches", C.c_int64), ("decoder_ms", C.c_double),
                 ("forward_launches", C.c_int64), ("forward_ms", C.c_double), ("jacobian_launches", C.c_int64),
                 ("jacobian_ms", C.c_double), ("tiles_forward", C.c_int64), ("tiles_jacobian", C.c_int64),
-                ("tiles_redone_forward", C.c_int64), ("tiles_redone_jacobian", C.c_int64)]
+                ("tiles_redone_forward", C.c_int64), ("tiles_redone_jacobian", C.c_int64),
+                ("rows_backward", C.c_int64), ("tiles_backward", C.c_int64), ("tiles_redone_backward", C.c_int64),
+                ("backward_launches", C.c_int64), ("backward_ms", C.c_double)]
 
 
 _lib = None
 
 # every symbol include/hortimapping_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_sparse_plan", "hm_plan_info", "hm_calibrate",
+EXPORTS = ["hm_last_error", "hm_version", "hm_create", "hm_destroy", "hm_set_engine", "hm_get_engine", "hm_set_sparse_plan", "hm_plan_info", "hm_set_mask_reuse", "hm_calibrate",
            "hm_get_counters", "hm_saturation_count", "hm_profile_enable", "hm_sdf_forward", "hm_sdf_forward_rows", "hm_sdf_jacobian", "hm_sdf_jacobian_rows",
            "hm_voxel_grid", "hm_sdf_grid", "hm_sdf_loss", "hm_render_loss", "hm_optimize_shape", "hm_optimize_joint",
            "hm_get_last_system", "hm_optimize_shape_host", "hm_optimize_joint_host", "hm_isosurface", "hm_isosurface_fetch", "hm_nn_distance", "hm_frame_id_bboxes", "hm_crop_candidates", "hm_gather_rays",
@@ -85,6 +87,7 @@ def bind(L: C.CDLL) -> C.CDLL:
     L.hm_get_engine.argtypes = [C.c_void_p]
     L.hm_set_sparse_plan.argtypes = [C.c_void_p, C.c_int]
     L.hm_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.hm_set_mask_reuse.argtypes = [C.c_void_p, C.c_int]
     L.hm_calibrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hm_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.hm_profile_enable.argtypes = [C.c_void_p, C.c_int]

@@ -155,6 +155,12 @@ extern "C" int hm_set_sparse_plan(hm_context* ctx, int on) {
   return HM_OK;
 }
 
+extern "C" int hm_set_mask_reuse(hm_context* ctx, int on) {
+  HM_CHECK(ctx, "hm_set_mask_reuse: null context");
+  ctx->mask_reuse = on ? 1 : 0;
+  return HM_OK;
+}
+
 extern "C" int hm_plan_info(const hm_context* ctx, double* h_out) {
   HM_CHECK(ctx && h_out, "hm_plan_info: null argument");
   hm_tc_plan_info(ctx, h_out);
@@ -171,7 +177,8 @@ extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
     HM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
     ctx->counters.decoder_ms += ms;
     ctx->counters.decoder_launches += 1;
-    if (ctx->prof_kinds[i / 2]) { ctx->counters.jacobian_ms += ms; ctx->counters.jacobian_launches += 1; }
+    if (ctx->prof_kinds[i / 2] == 2) { ctx->counters.backward_ms += ms; ctx->counters.backward_launches += 1; }
+    else if (ctx->prof_kinds[i / 2]) { ctx->counters.jacobian_ms += ms; ctx->counters.jacobian_launches += 1; }
     else { ctx->counters.forward_ms += ms; ctx->counters.forward_launches += 1; }
     ctx->prof_pool.push_back(ctx->prof_events[i]);
     ctx->prof_pool.push_back(ctx->prof_events[i + 1]);
@@ -180,7 +187,7 @@ extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
   ctx->prof_kinds.clear();
   *out = ctx->counters;
   if (ctx->d_tc_flags) {      // exact device-side totals of the tensor-core engine (HM_TC_FLAG_* slots, common.cuh)
-    unsigned long long dev[6] = {};
+    unsigned long long dev[9] = {};
     HM_CUDA(cudaMemcpy(dev, ctx->d_tc_flags + HM_TC_FLAG_ROWS_FWD, sizeof(dev), cudaMemcpyDeviceToHost));
     out->rows_forward += (int64_t)dev[0];
     out->rows_jacobian += (int64_t)dev[1];
@@ -188,6 +195,9 @@ extern "C" int hm_get_counters(hm_context* ctx, hm_counters* out) {
     out->tiles_jacobian = (int64_t)dev[3];
     out->tiles_redone_forward = (int64_t)dev[4];
     out->tiles_redone_jacobian = (int64_t)dev[5];
+    out->rows_backward = (int64_t)dev[6];
+    out->tiles_backward = (int64_t)dev[7];
+    out->tiles_redone_backward = (int64_t)dev[8];
   }
   return HM_OK;
 }
@@ -247,7 +257,7 @@ int hm_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_jac, 
     HM_CUDA(cudaEventRecord(e1, st));
     ctx->prof_events.push_back(e0);
     ctx->prof_events.push_back(e1);
-    ctx->prof_kinds.push_back(d_jac ? 1 : 0);
+    ctx->prof_kinds.push_back(rows.d_mask_in ? 2 : d_jac ? 1 : 0);
   }
   return rc;
 }

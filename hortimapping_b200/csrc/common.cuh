@@ -51,6 +51,9 @@ void hm_set_error(const char* fmt, ...);
 #define HM_TC_FLAG_TILES_JAC 8
 #define HM_TC_FLAG_DEAD_FWD 10      // ... of which failed the sparse plan's checks and were re-evaluated with the full plan
 #define HM_TC_FLAG_DEAD_JAC 12
+#define HM_TC_FLAG_ROWS_BWD 14      // rows / tiles / re-evaluated tiles of gradient-only launches (stored ReLU masks)
+#define HM_TC_FLAG_TILES_BWD 16
+#define HM_TC_FLAG_DEAD_BWD 18
 #define HM_TC_FLAG_DEBUG 32         // wait-cycle counters of the instrumented testing build (HM_TC_COUNTERS)
 #define HM_TC_FLAG_COUNT 128
 
@@ -106,6 +109,7 @@ struct hm_context {
   uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
   int32_t* d_tc_flags = nullptr;   // saturation counter etc.
   uint32_t* d_tc_trace = nullptr;  // timeline buffer of the instrumented testing build (NULL in the product)
+  int mask_reuse = 1;              // joint loop: gradient of the in-band samples from the forward pass's ReLU bits (hm_set_mask_reuse)
   int sparse_plan = 1;             // tensor-core engine: use the calibrated sparse plan (hm_set_sparse_plan); 0 = full plan always
   // grow-only workspace
   void* ws = nullptr;
@@ -173,6 +177,11 @@ struct hm_rows {
   const int32_t* d_n_dynamic;   // optional device-side row count (<= n); NULL = use n
   const int32_t* d_out_index = nullptr;   // optional: the SDF of row i goes to d_sdf[d_out_index[i]] (rows compacted from a larger set)
   int32_t* d_latent_sat = nullptr;        // optional [L]: the tensor-core engine sets entry l when a row of latent-table row l saturated fp16
+  // tensor-core engine only.  Forward-only call: store the ReLU bits of all 8 layers per 64-row tile ([tile][8][512][2] words).
+  uint32_t* d_mask_out = nullptr;
+  // Gradient-only call (d_jac given, d_sdf is an INPUT): the stored bits and, per row, the row index it had in the call that stored them.
+  const uint32_t* d_mask_in = nullptr;
+  const int32_t* d_src_row = nullptr;
   // fused mesher grid (wild_completion/utils.py:542-562): when grid_n > 0 the xyz of row i is create_voxel_grid(grid_n)[i] *
   // grid_radius, generated inside the decoder kernel (d_xyz is ignored; all rows use latent 0)
   int32_t grid_n = 0;

@@ -87,6 +87,9 @@ struct TcParams {
   uint32_t* trace;            // timeline of the first CTA pair (testing build only) or null
   int32_t grid_n;             // > 0: xyz of row i = voxel grid point i (fused mesher grid, hm_rows)
   float grid_voxel, grid_radius;
+  uint32_t* mask_out;         // forward-only pass: optional per-TILE store of the 8 layers' ReLU masks, [tile][8][512 threads][2 words]
+  const uint32_t* mask_in;    // backward-only pass (kMode 2): the masks a forward-only pass stored, and ...
+  const int32_t* src_row;     // ... [n] the row index each row had in THAT pass (its tile = src / 64, its point = src % 64)
   int32_t* redo;              // [0] = number of queued tiles, [4 ..] = tile indices: appended by the sparse pass, read by the redo pass
   // lin8 weight (permuted unit order).  Every lane of an epilogue warp reads the SAME columns, so the kernel-parameter constant
   // bank serves it at register speed; a global load in the finalize loop is an exposed L2 round trip (the L1 is ~0 KB here).
@@ -125,8 +128,17 @@ __device__ __forceinline__ bool stage_used(const hm_tc_op& o, int step, int whic
 // kRedo = false: tiles 2 * unit + rank, evaluated with P.plan (the sparse plan); a tile whose activations contradict the
 // plan's zero-chunk assumptions is appended to P.redo.  kRedo = true: the tiles listed in P.redo, evaluated with P.plan = the
 // full plan (launched right behind the first kernel; exits at once when the list is empty).
-template <bool kJac, bool kRedo>
+//
+// kMode 0: forward only (optionally storing the ReLU masks per tile, P.mask_out).  kMode 1: forward + input gradient.
+// kMode 2: input gradient ONLY, for rows a forward-only pass has already evaluated (the joint loop's in-band ray samples,
+// loss.py:185-215): the backward pass needs nothing of the forward pass but the ReLU bits and the SDF value, so the tile starts at
+// B7 with d7 = w8 * relu'(h7) rebuilt from the stored bits -- the same operand F7's epilogue writes in kMode 1, hence the same bits
+// out -- and P.sdf is an input.
+template <int kMode, bool kRedo>
 __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_constant__ TcParams P) {
+  constexpr bool kJac = kMode != 0;
+  constexpr bool kBwd = kMode == 2;
+  constexpr int kOpBegin = kBwd ? 8 : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int CG = 2;
   constexpr int kStages = kMaxStages;
@@ -188,11 +200,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   if (lane == 0 && (warp == 1 || warp == kCtrlWarps)) HM_TRACE(warp == 1 ? 0 : 1 + rank, 0, 0, 0);     // common time origin
 
   if (!kRedo && blockIdx.x == 0 && threadIdx.x == 0) {     // exact row / tile accounting for the roofline (rows actually evaluated)
-    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_ROWS_JAC : HM_TC_FLAG_ROWS_FWD)), (unsigned long long)n_rows);
-    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_TILES_JAC : HM_TC_FLAG_TILES_FWD)), (unsigned long long)n_tiles);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kBwd ? HM_TC_FLAG_ROWS_BWD : kJac ? HM_TC_FLAG_ROWS_JAC : HM_TC_FLAG_ROWS_FWD)), (unsigned long long)n_rows);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kBwd ? HM_TC_FLAG_TILES_BWD : kJac ? HM_TC_FLAG_TILES_JAC : HM_TC_FLAG_TILES_FWD)), (unsigned long long)n_tiles);
   }
   if (kRedo && blockIdx.x == 0 && threadIdx.x == 0)
-    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kJac ? HM_TC_FLAG_DEAD_JAC : HM_TC_FLAG_DEAD_FWD)), (unsigned long long)n_tiles);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kBwd ? HM_TC_FLAG_DEAD_BWD : kJac ? HM_TC_FLAG_DEAD_JAC : HM_TC_FLAG_DEAD_FWD)), (unsigned long long)n_tiles);
   const int64_t n_units = (n_tiles + 1) / 2;               // a unit = one tile per CTA of the pair
 
   if (warp < kCtrlWarps) {
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     uint32_t slot = 0, phase = 0;
     long long t_empty = 0;
     for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-      for (int op = 0; op < kOps; ++op) {
+      for (int op = kOpBegin; op < kOps; ++op) {
         const hm_tc_op& o = P.plan.ops[op];
         const uint32_t gm = o.group_mask;
         if (gm == 0u) continue;
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       const long long t_begin = clock64();
 #endif
       for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-        for (int op = 0; op < kOps; ++op) {
+        for (int op = kOpBegin; op < kOps; ++op) {
           const hm_tc_op& o = P.plan.ops[op];
           const uint32_t gm = o.group_mask;
           if (gm == 0u) continue;                  // op dropped by the plan: the epilogue warps produce no A operand (and no A_READY phase) for it
@@ -405,8 +417,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       const bool ok = tile >= 0 && grow < n_rows;
       const int64_t lr = ok ? grow : n_rows - 1;
       const float* const lat_ptr = lat_ptr_of(lr, cur_li);
+      float f_out = 0.f, c7 = 0.f;
+      bool viol = false;                     // a forward op found a live unit where the sparse plan assumes zeros
+      // where this tile's ReLU masks are written (forward ops) and read (backward ops): [op][thread][2 words]
+      uint32_t* mask_wr = my_masks;
+      const uint32_t* mask_rd = my_masks;
+      if (kMode == 0 && P.mask_out && tile >= 0) mask_wr = P.mask_out + (size_t)tile * 8 * kMaskStride + (size_t)(e_w * 32 + lane) * 2;
+      if constexpr (!kBwd) {
       // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group g8 writes k in [8*g8, +8)
-      {
         const float s0 = P.plan.ops[0].in_scale;
         float xin[8];
 #pragma unroll
@@ -422,17 +440,49 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         for (int e = 0; e < 4; ++e) store_pair(smem, 0, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat);
         publish(cq >> 1);                        // every warp arrives once per k-step of its own chunks' parity (see finalize)
         publish(2 + (cq >> 1));
+      } else {
+        // ---- backward-only tile: the masks of this thread's point sit where the forward-only pass stored them -- in the slot of
+        //      the thread that owned the SAME column group of that point there (sub-partition 2 * hq + point / 32, lane point % 32)
+        const int32_t src = __ldg(P.src_row + lr);
+        const int32_t sp_src = 2 * hq + ((src & 63) >> 5);
+        mask_rd = P.mask_in + (size_t)(src >> 6) * 8 * kMaskStride + (size_t)((4 * cq + sp_src) * 32 + (src & 31)) * 2;
+        uint2 mk[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) mk[l] = __ldg(reinterpret_cast<const uint2*>(mask_rd + (size_t)l * kMaskStride));     // 8 independent loads
+        f_out = __ldg(P.sdf + lr);
+        c7 = 1.f - f_out * f_out;                // tanh' (deep_sdf_decoder.py:107-108)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {            // the sparse plan's assumptions, checked on the stored bits
+          const uint32_t va = P.plan.ops[l].verify_alive;
+          if ((!((va >> chunk_lo) & 1u) && mk[l].x != 0u) || (!((va >> (4 + chunk_lo)) & 1u) && mk[l].y != 0u)) viol = true;
+        }
+        // A operand of B7: d7 = w8 * relu'(h7) (what F7's epilogue writes when forward and gradient run in one pass)
+        const float s_in = P.plan.ops[8].in_scale;
+        const uint32_t need7 = P.plan.ops[7].need_out;
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh) {
+          if ((need7 >> (4 * nh + chunk_lo)) & 1u) {
+            const uint32_t mbits = nh ? mk[7].y : mk[7].x;
+            const float* w8 = P.w8 + col0_of(nh);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float r[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = ((mbits >> (8 * u + i)) & 1u) ? w8[8 * u + i] * s_in : 0.f;
+              emit_unit(nh, u, r);
+            }
+          }
+          publish(2 * nh + (cq >> 1));
+        }
       }
-      float f_out = 0.f, c7 = 0.f;
       // Accumulators of this thread: acc[nh][i] = columns col0_of(nh) + 2i + {0, 1}.
       float2 acc[2][16];
       uint32_t m0 = 0u, m1 = 0u;             // ReLU bits of the current op: output half 0 / half 1, bit j = column col0 + j
       float dot = 0.f;
-      bool viol = false;                     // a forward op found a live unit where the sparse plan assumes zeros
       const std::integral_constant<int, 0> I0{};
       const std::integral_constant<int, 1> I1{};
 #pragma unroll 1
-      for (int op = 0; op < kOps; ++op) {
+      for (int op = kOpBegin; op < kOps; ++op) {
         const hm_tc_op& o = P.plan.ops[op];
         const uint32_t gm = o.group_mask;
         if (gm == 0u) continue;                          // dropped by the plan (its A operand is exactly zero)
@@ -442,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns (32 TMEM columns), one group per step
         const bool wide = (o.n_kchunks != 1);
         const bool fwd_op = op < 8;
-        if (op == last_op && unit + unit_stride < n_units) {      // next tile: latent-table row now, x0 lines into L2
+        if (!kBwd && op == last_op && unit + unit_stride < n_units) {      // next tile: latent-table row now, x0 lines into L2
           const int64_t nr = row_of(tile_of(unit + unit_stride));
           nxt_li = latent_row_of(nr);
           if (!P.rows && P.grid_n == 0 && g8 == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.xyz + nr * 3));
@@ -455,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const bool emit0 = (need >> chunk_lo) & 1u, emit1 = (need >> (4 + chunk_lo)) & 1u;
         m0 = m1 = 0u;
         if (kJac && op >= 8 && op < 15 && !o.is_last) {
-          const uint2 mw = *reinterpret_cast<const uint2*>(my_masks + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
+          const uint2 mw = *reinterpret_cast<const uint2*>(mask_rd + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
           m0 = mw.x; m1 = mw.y;
         }
         // collect the partial accumulator of one (step, n-half) group.  FIRST: the group opens the op for this output half
@@ -683,13 +733,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             if (gm & 128u) promote(I1, I0);
           }
           finalize(I1, op, k_mul, unscale, s_next, m1);
-          if (kJac && op < 7) *reinterpret_cast<uint2*>(my_masks + (size_t)op * kMaskStride) = make_uint2(m0, m1);
+          if ((kMode == 1 && op < 7) || (kMode == 0 && P.mask_out && op < 8)) *reinterpret_cast<uint2*>(mask_wr + (size_t)op * kMaskStride) = make_uint2(m0, m1);
         }
         // ---- lin8 + tanh (deep_sdf_decoder.py:107-108): every thread sums the 8 column-group partials of its point.  A forward-only
         //      pass does it at the end of F7 (= the end of the tile).  With the gradient requested it is DEFERRED to the end of B7's
         //      epilogue: nothing needs the SDF or tanh' before the last gradient op, and here it would sit between F7's last finalize
         //      and B7's first promotion, i.e. on the critical path of the op chain; there it runs while the tensor core works on B6.
-        if ((!kJac && op == 7) || (kJac && op == 8)) {
+        if ((kMode == 0 && op == 7) || (kMode == 1 && op == 8)) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
           dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -925,10 +975,12 @@ int hm_tc_init(hm_context* ctx) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * HM_TC_FLAG_COUNT));
     HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * HM_TC_FLAG_COUNT));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    HM_CUDA(cudaFuncSetAttribute(tc_decoder_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   }
   std::vector<float> bias(8 * HM_HIDDEN, 0.f);
   for (int l = 0; l < 8; ++l) {
@@ -1012,6 +1064,11 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.grid_voxel = rows.grid_voxel;
   P.grid_radius = rows.grid_radius;
   P.redo = nullptr;
+  P.mask_out = d_jac ? nullptr : rows.d_mask_out;
+  P.mask_in = rows.d_mask_in;
+  P.src_row = rows.d_src_row;
+  const int mode = rows.d_mask_in ? 2 : d_jac ? 1 : 0;
+  HM_CHECK(mode != 2 || (d_jac && d_sdf && rows.d_src_row), "gradient-only decode needs the Jacobian output, the SDF input and the source-row table");
   const int64_t n_tiles = (rows.n + HM_TC_TILE_M - 1) / HM_TC_TILE_M;
   const int csize = 2;                                              // the kernel is a CTA-pair kernel
   const int64_t n_units = (n_tiles + csize - 1) / csize;             // a unit = one 64-row tile per CTA of the cluster
@@ -1040,14 +1097,16 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, false>, P));
-  else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, false>, P));
+  if (mode == 2) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<2, false>, P));
+  else if (mode == 1) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<1, false>, P));
+  else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<0, false>, P));
   ctx->counters.kernel_launches += 1;
   if (sparse) {
     // second pass: the queued tiles with the full plan (the kernel returns at once when the queue is empty)
     P.plan = ctx->tc_plan_full;
-    if (d_jac) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<true, true>, P));
-    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<false, true>, P));
+    if (mode == 2) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<2, true>, P));
+    else if (mode == 1) HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<1, true>, P));
+    else HM_CUDA(cudaLaunchKernelEx(&cfg, tc_decoder_kernel<0, true>, P));
     ctx->counters.kernel_launches += 1;
   }
   HM_CUDA(cudaGetLastError());

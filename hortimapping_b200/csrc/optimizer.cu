@@ -122,7 +122,8 @@ __global__ void frame_setup_kernel(int n_frames, FrameState* __restrict__ fs, co
 __global__ void __launch_bounds__(256) sample_kernel(int64_t n_samples, int M, FrameState* __restrict__ fs, const int32_t* __restrict__ ray_frame,
                                                      const float* __restrict__ rays, const uint8_t* __restrict__ active, float* __restrict__ xyz,
                                                      uint8_t* __restrict__ valid, float* __restrict__ xyz_c, int32_t* __restrict__ idx_c,
-                                                     int32_t* __restrict__ row_latent_c, int32_t* __restrict__ n_valid_total) {
+                                                     int32_t* __restrict__ row_latent_c, int32_t* __restrict__ n_valid_total,
+                                                     int32_t* __restrict__ cidx_of /* [n_samples] or NULL: sample -> compact row */) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool v = false;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256) sample_kernel(int64_t n_samples, int M, F
     xyz_c[(int64_t)slot * 3 + 2] = p[2];
     idx_c[slot] = (int32_t)i;
     row_latent_c[slot] = fruit;
+    if (cidx_of) cidx_of[i] = slot;
   }
 }
 
@@ -299,14 +301,19 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int n_blocks, const i
     if (threadIdx.x == 1023) carry += s[1023];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_rows_dyn = n_static_rows + carry;
+  if (threadIdx.x == 0) {
+    n_rows_dyn[0] = n_static_rows + carry;       // all gradient rows: observed points + in-band samples
+    n_rows_dyn[1] = carry;                       // the in-band samples alone
+  }
 }
 
 // scatter the surviving samples into the compact grad-row list (after the static recon rows)
 __global__ void scatter_kernel(int64_t n_rays, int M, const int32_t* __restrict__ ray_frame, const FrameState* __restrict__ fs,
                                const unsigned long long* __restrict__ ray_mask, const int32_t* __restrict__ ray_off_in_block,
                                const int32_t* __restrict__ block_base, const float* __restrict__ xyz_s, int32_t n_static_rows,
-                               float* __restrict__ xyz_g, int32_t* __restrict__ row_latent_g, int32_t* __restrict__ ray_slot) {
+                               float* __restrict__ xyz_g, int32_t* __restrict__ row_latent_g, int32_t* __restrict__ ray_slot,
+                               const int32_t* __restrict__ cidx_of, const float* __restrict__ sdf_s, int32_t* __restrict__ src_g,
+                               float* __restrict__ sdf_g) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rays) return;
   unsigned long long keep = ray_mask[r];
@@ -321,6 +328,10 @@ __global__ void scatter_kernel(int64_t n_rays, int M, const int32_t* __restrict_
     xyz_g[(int64_t)slot * 3 + 1] = xyz_s[s * 3 + 1];
     xyz_g[(int64_t)slot * 3 + 2] = xyz_s[s * 3 + 2];
     row_latent_g[slot] = fruit;
+    if (src_g) {        // gradient-only decode of this row: where the forward pass evaluated it, and the SDF it got there
+      src_g[slot - n_static_rows] = cidx_of[s];
+      sdf_g[slot] = sdf_s[s];
+    }
     ++slot;
   }
 }
@@ -975,7 +986,11 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
     float* xyz_c; int32_t *idx_c, *row_latent_c, *n_valid;
     int32_t *ray_k, *ray_off, *ray_slot, *block_sum, *block_base, *n_rows_dyn;
     float *xyz_g, *sdf_g, *jac_g; int32_t* row_latent_g; float *J_d, *J_m, *J_r, *res_r, *partials; int32_t *block_items, *fruit_sat;
+    int32_t *cidx_of, *src_g; uint32_t* masks;
   } w;
+  // the forward pass over the ray samples keeps its ReLU bits (512 B per row) so that the gradient of the in-band samples does not
+  // need a second forward evaluation (hm_set_mask_reuse)
+  const bool reuse = joint && n_rays > 0 && ctx->engine == HM_ENGINE_TC && ctx->mask_reuse;
   auto carve = [&](void* base) {
     Carver c(base);
     w.fs = c.take<FrameState>(n_frames); w.ray_frame = c.take<int32_t>(n_rays); w.point_fruit = c.take<int32_t>(n_points);
@@ -989,6 +1004,8 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
     w.xyz_g = c.take<float>(Gmax * 3); w.sdf_g = c.take<float>(Gmax); w.jac_g = c.take<float>(Gmax * HM_IN); w.row_latent_g = c.take<int32_t>(Gmax);
     w.J_d = c.take<float>(n_rays * kE); w.J_m = c.take<float>(n_rays * kE); w.J_r = c.take<float>(n_points * kE); w.res_r = c.take<float>(n_points);
     w.partials = c.take<float>((size_t)n_blocks * kPartial); w.block_items = c.take<int32_t>(n_blocks); w.fruit_sat = c.take<int32_t>(nf);
+    w.cidx_of = c.take<int32_t>(reuse ? S : 0); w.src_g = c.take<int32_t>(reuse ? S : 0);
+    w.masks = c.take<uint32_t>(reuse ? (size_t)((S + HM_TC_TILE_M - 1) / HM_TC_TILE_M) * 8 * 1024 : 0);
     return c.off + 256;
   };
   const size_t need = carve(nullptr);
@@ -1037,29 +1054,42 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
     if (joint && n_rays > 0) {
       frame_setup_kernel<<<nblk(n_frames, 64), 64, 0, st>>>(n_frames, w.fs, b->d_T_ow, b->d_T_wc, w.cube_radius, w.active, M, w.n_valid);
       sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, b->d_rays, w.active, w.xyz_s, w.valid, w.xyz_c, w.idx_c,
-                                                  w.row_latent_c, w.n_valid);
+                                                  w.row_latent_c, w.n_valid, reuse ? w.cidx_of : nullptr);
       launches += 2;
       // forward pass over the in-sphere samples only (loss.py:47-49); the SDF of compact row j lands at sample idx_c[j]
       hm_rows srows = {nullptr, w.xyz_c, b->d_latents, w.row_latent_c, S, w.n_valid};
       srows.d_out_index = w.idx_c;
       srows.d_latent_sat = w.fruit_sat;
+      srows.d_mask_out = reuse ? w.masks : nullptr;
       rc = hm_decode(ctx, srows, w.sdf_s, nullptr, st);
       if (rc) return rc;
       composite_kernel<<<n_scan_blocks, 256, 0, st>>>(n_rays, P, w.fs, w.ray_frame, b->d_depth_obs, w.valid, w.sdf_s, w.active, w.coef_e,
                                                       w.coef_m, w.ray_mask, w.res_d, w.res_m, w.ray_k, w.ray_off, w.block_sum, b->d_status);
       scan_blocks_kernel<<<1, 1024, 0, st>>>(n_scan_blocks, w.block_sum, w.block_base, w.n_rows_dyn, (int32_t)n_points);
       scatter_kernel<<<nblk(n_rays, 256), 256, 0, st>>>(n_rays, M, w.ray_frame, w.fs, w.ray_mask, w.ray_off, w.block_base, w.xyz_s,
-                                                        (int32_t)n_points, w.xyz_g, w.row_latent_g, w.ray_slot);
+                                                        (int32_t)n_points, w.xyz_g, w.row_latent_g, w.ray_slot, w.cidx_of, w.sdf_s,
+                                                        reuse ? w.src_g : nullptr, w.sdf_g);
       launches += 3;
-      grows.n = Gmax;
-      grows.d_n_dynamic = w.n_rows_dyn;
+      if (!reuse) {
+        grows.n = Gmax;
+        grows.d_n_dynamic = w.n_rows_dyn;
+      }
     }
     if (n_points > 0) {
       transform_points_kernel<<<nblk(n_points, 256), 256, 0, st>>>(n_points, w.point_fruit, b->d_points_w, b->d_T_ow, w.xyz_g, w.row_latent_g);
       ++launches;
     }
-    rc = hm_decode(ctx, grows, w.sdf_g, w.jac_g, st);
+    rc = hm_decode(ctx, grows, w.sdf_g, w.jac_g, st);       // observed points (+ the in-band samples when the forward pass is not reused)
     if (rc) return rc;
+    if (reuse) {
+      // in-band samples: gradient only, from the ReLU bits and SDF values of the forward launch above
+      hm_rows brows = {nullptr, w.xyz_g + n_points * 3, b->d_latents, w.row_latent_g + n_points, S, w.n_rows_dyn + 1};
+      brows.d_latent_sat = w.fruit_sat;
+      brows.d_mask_in = w.masks;
+      brows.d_src_row = w.src_g;
+      rc = hm_decode(ctx, brows, w.sdf_g + n_points, w.jac_g + n_points * HM_IN, st);
+      if (rc) return rc;
+    }
     if (joint && n_rays > 0) {
       ray_jacobian_kernel<<<nblk(n_rays, 128), 128, 0, st>>>(n_rays, M, pose_dim, w.ray_mask, w.ray_slot, w.coef_e, w.coef_m, w.xyz_g, w.jac_g, w.J_d, w.J_m);
       ++launches;
@@ -1246,7 +1276,7 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
   HM_CUDA(cudaMemsetAsync(w.active, 1, 4, st));
   HM_CUDA(cudaMemsetAsync(w.n_valid, 0, 16, st));
   HM_CUDA(cudaStreamSynchronize(st));
-  sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, d_rays, w.active, w.xyz_s, w.valid, w.xyz_c, w.idx_c, w.row_latent_c, w.n_valid);
+  sample_kernel<<<nblk(S, 256), 256, 0, st>>>(S, M, w.fs, w.ray_frame, d_rays, w.active, w.xyz_s, w.valid, w.xyz_c, w.idx_c, w.row_latent_c, w.n_valid, nullptr);
   hm_rows srows = {nullptr, w.xyz_c, d_latent, nullptr, S, w.n_valid};      // in-sphere samples only (loss.py:47-49)
   srows.d_out_index = w.idx_c;
   rc = hm_decode(ctx, srows, w.sdf_s, nullptr, st);
@@ -1255,7 +1285,7 @@ extern "C" int hm_render_loss(hm_context* ctx, const hm_opt_params* p, const flo
                                                   w.ray_mask, d_res_d, d_res_m, w.ray_k, w.ray_off, w.block_sum, w.status);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(n_scan_blocks, w.block_sum, w.block_base, w.n_rows_dyn, 0);
   scatter_kernel<<<nblk(n_rays, 256), 256, 0, st>>>(n_rays, M, w.ray_frame, w.fs, w.ray_mask, w.ray_off, w.block_base, w.xyz_s, 0, w.xyz_g,
-                                                    w.row_latent_g, w.ray_slot);
+                                                    w.row_latent_g, w.ray_slot, nullptr, nullptr, nullptr, nullptr);
   hm_rows grows = {nullptr, w.xyz_g, d_latent, nullptr, S, w.n_rows_dyn};
   rc = hm_decode(ctx, grows, w.sdf_g, w.jac_g, st);
   if (rc) return rc;

@@ -117,6 +117,11 @@ class Decoder:
         violators re-evaluated with the full plan); results are bit-identical either way."""
         check(self._L.hm_set_sparse_plan(self._h, int(bool(on))), "hm_set_sparse_plan")
 
+    def set_mask_reuse(self, on: bool):
+        """Joint loop: take the gradient of the in-band ray samples from the forward pass's stored ReLU bits instead of evaluating
+        those rows a second time (hm_set_mask_reuse); results are bit-identical either way."""
+        check(self._L.hm_set_mask_reuse(self._h, int(bool(on))), "hm_set_mask_reuse")
+
     def plan_info(self) -> dict:
         """Tensor-core FLOP the engine issues per row under the current calibration (hm_plan_info): sparse / full plan, forward /
         forward + gradient, and the number of 64-wide chunks of each hidden layer the sparse plan keeps."""

@@ -133,6 +133,11 @@ typedef struct hm_counters {
   int64_t tiles_jacobian;
   int64_t tiles_redone_forward;  /* ... of which contradicted the sparse plan and were re-evaluated with the full  */
   int64_t tiles_redone_jacobian; /*     plan (hm_set_sparse_plan; 0 for the shipped models on calibrated rows)     */
+  int64_t rows_backward;      /* decoder rows evaluated gradient-only from stored ReLU masks (hm_set_mask_reuse)  */
+  int64_t tiles_backward;
+  int64_t tiles_redone_backward;
+  int64_t backward_launches;  /* timed gradient-only launches and their CUDA-event durations                     */
+  double backward_ms;
 } hm_counters;
 
 const char* hm_last_error(void);
@@ -156,6 +161,13 @@ int hm_set_sparse_plan(hm_context* ctx, int on);
  * same with the full plan (three fp16 products per fp32 product, padding included), [4 .. 11] = 64-wide chunks of h_0 .. h_7 the
  * sparse plan treats as possibly non-zero (8 = no assumption).  h_out has 12 entries. */
 int hm_plan_info(const hm_context* ctx, double* h_out);
+/* Joint loop (hm_optimize_joint), tensor-core engine: reuse of the forward pass (on by default).  The reference evaluates the
+ * in-band ray samples twice per iteration -- once among all in-sphere samples (loss.py:47-49, no grad) and once more with autograd
+ * for the Jacobians (loss.py:185-215).  With the switch on, the forward launch stores every row's ReLU bits (512 B per row) and the
+ * gradient of the in-band samples comes from a gradient-only launch that starts from those bits and the SDF values already
+ * computed; only the observed points (loss.py:219-243) still need forward + gradient.  Same arithmetic on the same operands:
+ * results are bit-identical with the switch off; it exists for that test and for measurements. */
+int hm_set_mask_reuse(hm_context* ctx, int on);
 /* Choose the power-of-two fp16 operand scales of the TC engine from sample rows [n][35] (device). */
 int hm_calibrate(hm_context* ctx, const float* d_rows, int64_t n, void* stream);
 /* With profiling enabled every decoder kernel launch is bracketed by CUDA events on its stream; hm_get_counters synchronises the

@@ -30,9 +30,9 @@ hdr = rows[0]; iid, iname = hdr.index("ID"), hdr.index("Kernel Name")
 pick = {}
 for r in rows[2:]:
     n = r[iname]
-    # tc_decoder_kernel<kJac, kRedo>: the redo instantiations (second template argument 1) exit at once on these inputs
-    key = ("jac" if re.search(r"tc_decoder_kernel<(\(bool\))?1, (\(bool\))?0>", n) else "fwd" if re.search(r"tc_decoder_kernel<(\(bool\))?0, (\(bool\))?0>", n)
-           else "solve" if "solve_kernel" in n else "normal_eq" if "normal_eq" in n else None)
+    # tc_decoder_kernel<kMode, kRedo> (0 forward, 1 forward + gradient, 2 gradient only): the redo instantiations (second template argument 1) exit at once on these inputs
+    key = ("jac" if re.search(r"tc_decoder_kernel<(\(int\))?1, (\(bool\))?0>", n) else "fwd" if re.search(r"tc_decoder_kernel<(\(int\))?0, (\(bool\))?0>", n)
+           else "bwd" if re.search(r"tc_decoder_kernel<(\(int\))?2, (\(bool\))?0>", n) else "solve" if "solve_kernel" in n else "normal_eq" if "normal_eq" in n else None)
     if key and key not in pick: pick[key] = r[iid]
 for key, lid in pick.items():
     src = subprocess.run(["ncu", "-i", "/tmp/prof_all.ncu-rep", "--page", "source", "--csv", "--launch-skip", lid, "--launch-count", "1"], capture_output=True, text=True).stdout

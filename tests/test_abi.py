@@ -47,7 +47,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.OptParams) == 10 * 4 + 16 * 8
     assert ctypes.sizeof(_lib.FruitBatch) == 8 + 14 * 8
     assert ctypes.sizeof(_lib.DecoderDesc) == 3 * 4 + 9 * 4 * 2 + 4 + 9 * 8 * 2
-    assert ctypes.sizeof(_lib.Counters) == 14 * 8
+    assert ctypes.sizeof(_lib.Counters) == 19 * 8
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -226,6 +226,45 @@ def test_batch_equals_single_and_is_deterministic():
             assert torch.equal(lat[f], lat_s[f][0]) and torch.equal(T[f], T_s[f][0]), f
 
 
+def test_mask_reuse_is_bit_identical_and_saves_the_second_forward():
+    """Joint loop: the in-band ray samples are evaluated forward among all in-sphere samples and then differentiated
+    (loss.py:47-49, :185-215).  With hm_set_mask_reuse on (the default) the forward launch keeps every row's ReLU bits and a
+    gradient-only launch starts from them; with it off the in-band rows go through forward + gradient again, as in the reference.
+    Same operands, same products: states, iteration counts and the last LM system must be BIT-identical, and the row counters
+    must show where the rows went (observed points -> forward + gradient, in-band samples -> gradient only)."""
+    c = load_npz("fruit_wild")
+    c2 = load_npz("fruit_challenge")
+    cfg = zero_eps(cfg_of(c), 5)
+    opt, dec = make_opt(cfg)
+    fruits = [(c, False), (c2, False), (c, True)]
+    n_pts = sum(cc["points_w"].shape[0] for cc, _ in fruits)
+    res = {}
+    try:
+        for on in (True, False):
+            dec.set_mask_reuse(on)
+            lat = torch.stack([torch.from_numpy(cc["init_latent"].copy()) for cc, _ in fruits]).cuda()
+            T = torch.stack([torch.from_numpy(cc["init_T_ow"].copy()) for cc, _ in fruits]).cuda()
+            c0 = dec.counters()
+            _, _, iters, status = opt.shape_pose_joint_opt_batch(lat, T, [render_data_of(cc) for cc, _ in fruits], [cc["points_w"] for cc, _ in fruits],
+                                                                 [float(cc["cube_radius"]) for cc, _ in fruits], [pk for _, pk in fruits])
+            c1 = dec.counters()
+            H, b, dx = last_system(dec, 3, 39)
+            res[on] = (lat.clone(), T.clone(), iters.clone(), status.clone(), H, b, dx, {k: c1[k] - c0[k] for k in c1})
+    finally:
+        dec.set_mask_reuse(True)
+    a, z = res[True], res[False]
+    assert a[2].cpu().tolist() == [5, 5, 5]
+    for i in range(4):
+        assert torch.equal(a[i], z[i]), i
+    for i in (4, 5, 6):
+        np.testing.assert_array_equal(a[i], z[i])
+    da, dz = a[7], z[7]
+    assert dz["rows_backward"] == 0 and da["rows_backward"] > 0
+    assert da["rows_jacobian"] == 5 * n_pts                                    # only the observed points are evaluated forward + gradient
+    assert da["rows_jacobian"] + da["rows_backward"] == dz["rows_jacobian"]     # the same gradient rows either way
+    assert da["rows_forward"] == dz["rows_forward"]
+
+
 def test_invalid_submap_keeps_state():
     """No frame with >= 100 in-sphere samples -> "This submap is not valid": state untouched, iter_count 0
     (optimizer.py:139-141); other fruits of the batch are unaffected."""
@@ -318,7 +357,8 @@ def test_full_size_joint_step_replay_counts_membership_flips(case_name, model):
         assert int(iters.item()) == 1 and not (int(status.item()) & 0x40)
         H, b, dx = (t.cpu().numpy()[0] for t in opt.last_system(1))
         d_fwd = c1["rows_forward"] - c0["rows_forward"] - int(c["trace_rows_fwd"][i])
-        d_jac = c1["rows_jacobian"] - c0["rows_jacobian"] - int(c["trace_rows_jac"][i])
+        # gradient rows = observed points (forward + gradient) + in-band samples (gradient only, from the forward pass's ReLU bits)
+        d_jac = (c1["rows_jacobian"] - c0["rows_jacobian"]) + (c1["rows_backward"] - c0["rows_backward"]) - int(c["trace_rows_jac"][i])
         eH, eb = rel(H, c["trace_H"][i]), rel(b, c["trace_b"][i])
         if d_fwd == 0 and d_jac == 0:
             worst_clean = max(worst_clean, eH, eb)
