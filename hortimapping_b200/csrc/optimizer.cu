@@ -1075,7 +1075,8 @@ int hm_optimize_impl(hm_context* ctx, const hm_opt_params* p, const hm_fruit_bat
         grows.d_n_dynamic = w.n_rows_dyn;
       }
     }
-    if (n_points > 0) {
+    if (n_points > 0 && (joint || it == p->iter_offset)) {
+      // (the latent-only loop never changes T_ow, optimizer.py:343: its object-frame points are the same in every iteration)
       transform_points_kernel<<<nblk(n_points, 256), 256, 0, st>>>(n_points, w.point_fruit, b->d_points_w, b->d_T_ow, w.xyz_g, w.row_latent_g);
       ++launches;
     }
