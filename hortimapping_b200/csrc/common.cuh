@@ -104,7 +104,7 @@ struct hm_context {
   float h_w8p[HM_HIDDEN] = {};     // lin8 weight in the permuted unit order of the tensor-core engine (travels as a kernel parameter)
   float act_absmax[HM_TC_NOPS_ALL] = {};   // calibration result: max |A operand| per op
   std::vector<float> unit_max;             // calibration result: [8][512] largest activation of every hidden unit (0 = never alive)
-  float* d_tc_bias = nullptr;      // [8][512] biases of lin0..7 (lin3 padded with 0)
+  std::vector<float> h_tc_bias;    // [8][512] biases of lin0..7 in the engine's unit order, pre-scaled (lin3 padded with 0); kernel parameter
   float* d_w8 = nullptr;           // [512] lin8 weight, d_b8 scalar in d_b[8]
   uint8_t* d_tc_masks = nullptr;   // per-CTA ReLU mask scratch
   int32_t* d_tc_flags = nullptr;   // saturation counter etc.

@@ -70,7 +70,6 @@ struct TcParams {
   const uint8_t* blob;
   int64_t blob_bytes;         // size of one copy of the weight blob
   int32_t blob_copies;        // copies laid out back to back (CTAs spread over them)
-  const float* bias;          // [8][512]
   float b8;                   // lin8 bias
   const float* rows;          // [n][35] or null
   const float* xyz;           // [n][3]
@@ -94,8 +93,11 @@ struct TcParams {
   // lin8 weight (permuted unit order).  Every lane of an epilogue warp reads the SAME columns, so the kernel-parameter constant
   // bank serves it at register speed; a global load in the finalize loop is an exposed L2 round trip (the L1 is ~0 KB here).
   alignas(16) float w8[HM_HIDDEN];
+  // ... and so do the biases of lin0..7 ([8][512], pre-scaled for the next op): staging them in shared memory cost two CTA-wide
+  // barriers and one exposed L2 round trip per forward op
+  alignas(16) float bias[8 * HM_HIDDEN];
 };
-static_assert(sizeof(TcParams) <= 4096, "kernel parameters exceed the 4 KB every driver accepts");
+static_assert(sizeof(TcParams) <= 32764, "kernel parameters exceed the 32 KB limit of sm_70+ (CUDA >= 12.1)");
 
 // k-chunk order of an 8-chunk op: k-step s multiplies chunks {0,2}, {1,3}, {4,6}, {5,7}.  Steps 0,1 read the chunks that the
 // previous op's output half 0 becomes (0..3), steps 2,3 those of its half 1 (4..7).
@@ -156,8 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   auto bar = [&](int i) { return bars + 8u * i; };
   volatile uint32_t* const ctl = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars);        // control words (byte offsets kCtl*)
   volatile uint32_t* tmem_ptr_smem = ctl + kCtlTmemPtr / 4;
-  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups] (lin8 tail) ...
-  float* bias_s = dot_scratch;                                                // ... and, before it, the current forward op's 512 biases
+  float* dot_scratch = reinterpret_cast<float*>(smem + kSmemBars + 256);      // [64 points][8 column groups]: partial lin8 dot products
   constexpr int kOps = kJac ? HM_TC_NOPS_ALL : HM_TC_NOPS_FWD;
   const int last_op = kJac ? P.plan.last_op_jac : P.plan.last_op_fwd;         // last executed op of a tile
   const uint32_t rank = cluster_ctarank();                                    // 0 = leader (MMA issuer) of the pair
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           const bool may_live = (o.verify_alive >> (4 * nh + chunk_lo)) & 1u;      // may this thread's chunk hold non-zeros (forward ops)?
           if (opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
-            const float* bias = bias_s + col0;
+            const float* bias = P.bias + opx * HM_HIDDEN + col0;
             const float2 kk = make_float2(k_mul_x, k_mul_x);
             if (nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");      // k-step 0 first (see below)
 #pragma unroll
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             // ---------------- lin7 epilogue + the lin8 dot product (deep_sdf_decoder.py:107-108).  With the gradient requested
             // the A operand of B7 is written right here: d7 = w8 * relu'(h7) WITHOUT the tanh' factor (1 - sdf^2), which is a
             // per-row scalar that needs the whole dot product; it multiplies the finished gradient instead (see B4 / B0 below).
-            const float* bias = bias_s + col0;
+            const float* bias = P.bias + opx * HM_HIDDEN + col0;
             const float* w8 = P.w8 + col0;
             const float2 uu = make_float2(unscale_x, unscale_x);
             if (kJac && nh == 0 && cq >= 2) asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -699,13 +700,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         //      tensor core still works on half 1; F(1) runs under the next op's first four groups (they read chunks 0..3 only) --
         //      with four TMEM buffers the tensor core can be that far ahead of the promotions.  Groups the plan dropped (gm) are
         //      skipped; a half whose opening group is among them starts from zero (0 + x = x: the same bits as an overwrite).
-        if (op <= 7) {
-          // stage this op's biases in shared memory (L1 is ~0 KB next to 226 KB of shared memory: a global load in the finalize
-          // loop is an exposed L2 round trip)
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          bias_s[e_w * 32 + lane] = __ldg(P.bias + op * HM_HIDDEN + e_w * 32 + lane);
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        }
         if (!(gm & 1u)) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[0][i] = make_float2(0.f, 0.f);
@@ -740,13 +734,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         //      epilogue: nothing needs the SDF or tanh' before the last gradient op, and here it would sit between F7's last finalize
         //      and B7's first promotion, i.e. on the critical path of the op chain; there it runs while the tensor core works on B6.
         if ((kMode == 0 && op == 7) || (kMode == 1 && op == 8)) {
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // every warp is done with bias_s (same memory)
+          // (no barrier in front of the writes: every warp has read the previous tile's sums before it published that tile's first A
+          // operand, and no warp gets past its first promotion of this tile before all of them have published)
           dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           const float4 d0 = *reinterpret_cast<const float4*>(dot_scratch + p * 8), d1 = *reinterpret_cast<const float4*>(dot_scratch + p * 8 + 4);
           f_out = tanhf((((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w))) + P.b8);
-          // (no barrier behind the reads: the next writer of this memory is the bias staging of the next tile's F0, which starts
-          // with a barrier of its own)
           dot = 0.f;
           c7 = 1.f - f_out * f_out;                                             // tanh' (deep_sdf_decoder.py:107-108)
           if (g8 == 0 && ok) P.sdf[P.out_index ? (int64_t)__ldg(P.out_index + grow) : grow] = f_out;
@@ -970,8 +963,7 @@ int hm_tc_init(hm_context* ctx) {
   ctx->tc_blob_copies = copies;
   for (int c = 0; c < copies; ++c)
     HM_CUDA(cudaMemcpy(ctx->d_tc_blob + (size_t)c * blob.size(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
-  if (!ctx->d_tc_bias) {
-    HM_CUDA(cudaMalloc(&ctx->d_tc_bias, sizeof(float) * 8 * HM_HIDDEN));
+  if (!ctx->d_tc_masks) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * HM_TC_FLAG_COUNT));
     HM_CUDA(cudaMemset(ctx->d_tc_flags, 0, sizeof(int32_t) * HM_TC_FLAG_COUNT));
@@ -988,7 +980,7 @@ int hm_tc_init(hm_context* ctx) {
     if (l < 7)                                       // the F_l epilogue emits h_l * in_scale(F_{l+1}): fold the scale into the bias
       for (int c = 0; c < HM_HIDDEN; ++c) bias[l * HM_HIDDEN + c] *= plan.ops[l + 1].in_scale;
   }
-  HM_CUDA(cudaMemcpy(ctx->d_tc_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice));
+  ctx->h_tc_bias = bias;
   memcpy(ctx->h_w8p, Wp[8].data(), sizeof(float) * HM_HIDDEN);
   return HM_OK;
 }
@@ -1023,14 +1015,12 @@ void hm_tc_plan_info(const hm_context* ctx, double* out) {
 
 void hm_tc_free(hm_context* ctx) {
   if (ctx->d_tc_blob) cudaFree(ctx->d_tc_blob);
-  if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
   if (ctx->d_tc_masks) cudaFree(ctx->d_tc_masks);
   if (ctx->d_tc_flags) cudaFree(ctx->d_tc_flags);
   if (ctx->d_tc_trace) cudaFree(ctx->d_tc_trace);
   if (ctx->d_tc_redo) cudaFree(ctx->d_tc_redo);
   ctx->d_tc_trace = nullptr;
   ctx->d_tc_blob = nullptr;
-  ctx->d_tc_bias = nullptr;
   ctx->d_tc_masks = nullptr;
   ctx->d_tc_flags = nullptr;
   ctx->d_tc_redo = nullptr;
@@ -1044,7 +1034,7 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   P.blob = ctx->d_tc_blob;
   P.blob_bytes = (int64_t)ctx->tc_blob_bytes;
   P.blob_copies = ctx->tc_blob_copies;
-  P.bias = ctx->d_tc_bias;
+  memcpy(P.bias, ctx->h_tc_bias.data(), sizeof(P.bias));
   memcpy(P.w8, ctx->h_w8p, sizeof(P.w8));
   P.b8 = ctx->h_b[8][0];
   P.rows = rows.d_rows;

@@ -43,13 +43,13 @@ PY
   ls -la /tmp/prof_all.ncu-rep | tee -a gpurun_out/ncu_full.log
 fi
 if has memcheck; then
-  ( timeout -k 5 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_optimizer.py -m gpu -q -x \
+  ( HM_TEST_CAL_ROWS=16384 timeout -k 5 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_optimizer.py -m gpu -q -x \
       -k "sparse_plan or contradict or ragged or replay or batch_equals or mask_reuse or invalid_submap or degenerate" 2>&1 | tail -15 ) > gpurun_out/sanitizer_memcheck.log; tail -4 gpurun_out/sanitizer_memcheck.log
 fi
 if has racecheck; then
-  ( timeout -k 5 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py -m gpu -q -x \
+  ( HM_TEST_CAL_ROWS=16384 timeout -k 5 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_decoder.py -m gpu -q -x \
       -k "ragged and (129 or 1000)" > /tmp/racecheck_full.log 2>&1 )
-  ( timeout -k 5 300 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_optimizer.py -m gpu -q -x \
+  ( HM_TEST_CAL_ROWS=16384 timeout -k 5 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_optimizer.py -m gpu -q -x \
       -k "mask_reuse" >> /tmp/racecheck_full.log 2>&1 )
   python scripts/summarise_racecheck.py /tmp/racecheck_full.log > gpurun_out/sanitizer_racecheck.log 2>&1; tail -12 gpurun_out/sanitizer_racecheck.log
 fi

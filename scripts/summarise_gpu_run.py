@@ -71,8 +71,30 @@ if os.path.exists(rep):
     s = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_source_summary.py"), tmp, "30"], capture_output=True, text=True).stdout
     open(p("ncu_decoder_source_summary.txt"), "w").write(s)
 
+# 3b. the dominant kernel of the headline workload from the all-kernel capture (scripts/ncu_target.py): tc_decoder_kernel<1, 0> over
+#     64 fruits x 2048 points = 131 072 rows per launch, exactly the bench's launch -> DRAM traffic and tensor-pipe activity per launch
+f = os.path.join(OUT, "ncu_kernels_raw.csv")
+if os.path.exists(f):
+    import re
+    rows = list(csv.reader(open(f)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}
+    val = lambda r, k: float(r[col[k]].replace(",", "")) * scale.get(units[col[k]], 1.0)
+    dom = [r for r in data if re.search(r"tc_decoder_kernel<(\(int\))?1, (\(bool\))?0>", r[col["Kernel Name"]])]
+    if dom:
+        tmax = max(val(r, "gpu__time_duration.sum") for r in dom)
+        big = [r for r in dom if val(r, "gpu__time_duration.sum") > 0.7 * tmax]
+        json.dump({"dram_bytes_per_launch": sum(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") for r in big) / len(big),
+                   "tensor_pipe_active_pct": sum(val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed") for r in big) / len(big),
+                   "duration_ms_under_ncu": sum(val(r, "gpu__time_duration.sum") for r in big) / len(big) * 1e3,
+                   "rows_per_launch": 64 * 2048, "launches_averaged": len(big),
+                   "source": f"profiles/{tag}_ncu_kernels.txt (ncu --set full of scripts/ncu_target.py)", "kernel": big[0][col["Kernel Name"]]},
+                  open(os.path.join(PROF, "dominant_kernel_traffic.json"), "w"))
+
 # 4. small logs kept verbatim
-for name in ("pytest_gpu.log", "dbg_rate.log", "dbg_wait.log", "gpu.txt", "scale.log", "extra.log", "scale_n2.log"):
+for name in ("pytest_gpu.log", "dbg_wait.log", "gpu.txt", "extra.log", "ncu_kernels.txt", "ncu_source_fwd.txt", "ncu_source_jac.txt", "ncu_source_bwd.txt",
+             "ncu_source_normal_eq.txt", "ncu_source_solve.txt", "sanitizer_memcheck.log", "sanitizer_racecheck.log", "diag_parity.log", "probe_speed.log"):
     f = os.path.join(OUT, name)
     if os.path.exists(f):
         open(p(name.replace(".log", ".txt")), "w").write(open(f).read())

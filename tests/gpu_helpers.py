@@ -1,4 +1,6 @@
 """Helpers for the -m gpu tests: build the product decoder from the golden weights."""
+import os
+
 import numpy as np
 import torch
 
@@ -13,7 +15,8 @@ def pepper_decoder():
         W, b, codes = pepper_weights()
         dec = Decoder(W, b)
         from hortimapping_b200.decoder import calibration_rows
-        dec.calibrate(calibration_rows(codes, 0.15))          # the recipe config_decoder uses
+        # the recipe config_decoder uses (fewer rows under compute-sanitizer, where the fp32 calibration pass runs ~100x slower)
+        dec.calibrate(calibration_rows(codes, 0.15, n=int(os.environ.get("HM_TEST_CAL_ROWS", "262144"))))
         _cache["pepper"] = dec
     return _cache["pepper"]
 

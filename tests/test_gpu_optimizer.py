@@ -55,16 +55,20 @@ def test_lm_every_iteration_replayed_from_reference_state(case_name):
     est = (7 if cfg["opt"]["scale_on"] else 6) + 32
     n = c["trace_H"].shape[0]
     tol = 2e-4 if case_name == "fruit_wild" else 2e-3
+    clean_tol = 5e-4 if case_name == "fruit_wild" else 2e-3           # iterations without a membership flip
     flip_tol = 5e-3
-    eH, eb, edx, elat, eT = [], [], [], [], []
+    eH, eb, edx, elat, eT, flips = [], [], [], [], [], []
     rd = render_data_of(c)
+    orc = oracle_decoder(np.float32)
     for i in range(n):
         lat0 = c["init_latent"] if i == 0 else c[f"after{i}_latent"]
         T0 = c["init_T_ow"] if i == 0 else c[f"after{i}_T_ow"]
         lat = torch.from_numpy(lat0.copy()).cuda().reshape(1, 32)
         T = torch.from_numpy(T0.copy()).cuda().reshape(1, 4, 4)
+        c0 = dec.counters()
         _, _, iters, status = opt.shape_pose_joint_opt_batch(lat, T, [rd], [c["points_w"]], float(c["cube_radius"]), pk,
                                                              iter_offset=i, max_iter=1)
+        c1 = dec.counters()
         assert int(iters.item()) == 1
         H, b, dx = last_system(dec, 1, est)
         eH.append(rel(H[0], c["trace_H"][i]))
@@ -72,32 +76,25 @@ def test_lm_every_iteration_replayed_from_reference_state(case_name):
         edx.append(rel(dx[0], c["trace_dx"][i]))
         elat.append(rel(lat.cpu().numpy()[0], c[f"after{i + 1}_latent"]))
         eT.append(rel(T.cpu().numpy()[0], c[f"after{i + 1}_T_ow"]))
+        # sample membership (in-sphere, in-band, occlusion: hard thresholds): rows the oracle selects from the same state vs the
+        # rows the device evaluated (exact device-side counters)
+        tr = O.OptTrace()
+        O.shape_pose_joint_opt(orc, cfg, lat0.copy(), T0.copy(), rd, c["points_w"], float(c["cube_radius"]), pk, trace=tr, iter_offset=i)
+        d_rows = (c1["rows_forward"] - c0["rows_forward"] - tr.rows_fwd,
+                  (c1["rows_jacobian"] - c0["rows_jacobian"]) + (c1["rows_backward"] - c0["rows_backward"]) - tr.rows_grad)
+        flips.append(abs(d_rows[0]) + abs(d_rows[1]))
+    print(f"{case_name}: per-iteration membership flips {flips}; H errors {['%.1e' % e for e in eH]}; b errors {['%.1e' % e for e in eb]}")
+    clean = [i for i in range(n) if flips[i] == 0]
+    assert len(clean) >= n // 2, flips
+    # with the same samples selected, H and b are held to the tensor-core engine's per-step bound (one ReLU-kink row moves an
+    # entry of H by ~1e-4, bench.py joint parity); a flipped sample may move them by up to its own weight
+    assert max(eH[i] for i in clean) < clean_tol and max(eb[i] for i in clean) < clean_tol, (clean, eH, eb)
     assert eH[0] < tol and eb[0] < tol, (eH, eb)
     assert np.median(eH) < tol and max(eH) < flip_tol, eH
     assert np.median(eb) < tol and max(eb) < 4 * flip_tol, eb
     assert np.median(edx) < 20 * tol, edx
     assert np.median(elat) < 10 * tol and max(elat) < 10 * flip_tol, elat
     assert np.median(eT) < 10 * tol and max(eT) < flip_tol, eT
-
-
-def test_solve_matches_fp64_oracle_from_identical_state():
-    """dx of the device solve (fp64 elimination) against the fp64 oracle from the same state: the reference's
-    own fp32 `torch.inverse` is the less accurate of the two (cond(H) ~ 1e5)."""
-    c = load_npz("fruit_wild")
-    cfg = zero_eps(cfg_of(c), 1)
-    opt, dec = make_opt(cfg)
-    rd = render_data_of(c)
-    lat = torch.from_numpy(c["init_latent"].copy()).cuda().reshape(1, 32)
-    T = torch.from_numpy(c["init_T_ow"].copy()).cuda().reshape(1, 4, 4)
-    opt.shape_pose_joint_opt_batch(lat, T, [rd], [c["points_w"]], float(c["cube_radius"]), False, max_iter=1)
-    H, b, dx = last_system(dec, 1, 39)
-    tr = O.OptTrace()
-    O.shape_pose_joint_opt(oracle_decoder(np.float64), cfg, c["init_latent"].astype(np.float64), c["init_T_ow"].astype(np.float64),
-                           rd, c["points_w"], float(c["cube_radius"]), False, trace=tr)
-    assert rel(H[0], tr.H[0]) < 1e-4
-    assert rel(b[0], tr.b[0]) < 1e-4
-    assert rel(dx[0], tr.dx[0]) < 1e-3
-    assert rel(lat.cpu().numpy()[0], tr.latent[0]) < 1e-4
 
 
 @pytest.mark.parametrize("var", ["se3", "lmeye", "linocc", "noocc", "gn"])
