@@ -39,11 +39,14 @@ import tempfile
 import threading
 import time
 
-if "reference" in sys.argv:
+if "reference" in sys.argv or "--impl=reference" in sys.argv:
     # the CPU arm uses every host core, also under torchrun (which exports OMP_NUM_THREADS=1 to each rank):
     # the BLAS thread pools read these variables when numpy / torch are imported
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count())
+    # ... and it must not see a GPU at all: the reference creates tensors on "cuda" in places the shim's `.cuda()` identity does not
+    # reach, so on a GPU box the CPU arm would end up with operands on two devices (this has to happen before torch is imported)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import numpy as np
 
