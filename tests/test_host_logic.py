@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import cfg_of, load_npz, render_data_of
+from tests.helpers import cfg_of, load_npz, pepper_weights, render_data_of
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -197,3 +197,23 @@ def test_checkpoint_loader_errors(tmp_path):
         load_decoder_weights(str(tmp_path))
     with pytest.raises(Exception, match="latent code file"):
         load_latent_vectors(str(tmp_path))
+
+
+def test_calibration_rows_cover_the_optimisers_working_region():
+    """decoder.calibration_rows: deterministic, [n][35] float32, latents on the segments between the mean training code (the initial
+    latent of every fruit, run_shape_completion_challenge.py:51-52) and the training codes plus a little jitter, a quarter of them the
+    training codes themselves; query points inside the requested cube."""
+    from hortimapping_b200.decoder import calibration_rows
+    codes = pepper_weights()[2]
+    a = calibration_rows(codes, 0.15, n=4096)
+    b = calibration_rows(torch.from_numpy(codes), 0.15, n=4096)
+    assert a.dtype == torch.float32 and tuple(a.shape) == (4096, 35) and torch.equal(a, b)
+    assert float(a[:, 32:].abs().max()) <= 0.15
+    z, mean = a[:, :32].numpy(), codes.mean(0)
+    # rows of the first quarter: a training code + N(0, 0.03) jitter
+    d = np.abs(z[:1024, None, :] - codes[None, :, :]).max(-1).min(-1)
+    assert d.max() < 0.2 and np.median(d) < 0.12
+    # the rest: within the jitter of the segment [mean, code] -> never farther from the mean than the farthest code (+ jitter)
+    r_codes = np.linalg.norm(codes - mean, axis=1).max()
+    assert np.linalg.norm(z - mean, axis=1).max() < r_codes + 0.03 * 6 * np.sqrt(32)
+    assert np.linalg.norm(z[1024:] - mean, axis=1).mean() < np.linalg.norm(z[:1024] - mean, axis=1).mean()
