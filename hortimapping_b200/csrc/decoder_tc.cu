@@ -26,6 +26,11 @@
 //     CHECKED, not trusted: each forward layer's epilogue looks at the ReLU bits of the columns the plan counts on being zero and
 //     a tile that contradicts it is queued and re-evaluated by a second launch of the same kernel with the full plan.  The
 //     dropped products are exact zeros, so sparse == full bit for bit.
+//   * three modes (template kMode): forward only (optionally storing every row's ReLU bits, 512 B per row), forward + gradient,
+//     and gradient ONLY from stored bits + SDF values (the joint loop differentiates a subset of the rows it has just evaluated,
+//     loss.py:185-215; the second forward evaluation the reference pays for them is not needed).
+//   * lin8's weight and the eight bias vectors travel in the kernel-parameter constant bank: every lane of an epilogue warp reads
+//     the same columns, so they arrive at register speed without shared-memory staging or barriers.
 //
 // Warp roles (640 threads): warpgroup 0 = control (warp 0 bulk-copy producer, warp 1 MMA issuer in the leader CTA / weight
 // arrival forwarder in the peer CTA + TMEM alloc, warps 2-3 idle), warpgroups 1-4 = 16 epilogue warps (4 per TMEM

@@ -80,10 +80,16 @@ def main():
             print("jac", jac, "ms", round(ms, 3), "(instrumented build) per-CTA avg cycles: total %.0f  wait_A %.1f%%  wait_part %.1f%%  wait_W %.1f%%  "
                   "(producer wait_empty %.1f%%)" % (tot / nlead, 100 * v[1] / tot, 100 * v[2] / tot, 100 * v[3] / tot, 100 * v[0] / tot))
     elif what == "trace":
-        dec._eval_rows(t, with_jac=True)
+        # PROBE_LATENT=1: one latent for all rows + an xyz array (the optimisers' input mode) instead of full [n][35] rows
+        if os.environ.get("PROBE_LATENT"):
+            lat1, xyz1 = t[0, :32].contiguous(), t[:, 32:].contiguous()
+            run = lambda: dec.sdf_jacobian(lat1, xyz1)
+        else:
+            run = lambda: dec._eval_rows(t, with_jac=True)
+        run()
         torch.cuda.synchronize()
         L.hm_debug_tc_trace(dec.handle, 1, None)
-        dec._eval_rows(t, with_jac=True)
+        run()
         torch.cuda.synchronize()
         out = np.zeros(3 * 8192 * 2, np.uint32)
         L.hm_debug_tc_trace(dec.handle, 0, out.ctypes.data)
