@@ -101,6 +101,26 @@ def test_lm_every_iteration_replayed_from_reference_state(case_name):
     assert np.median(eT) < 10 * tol and max(eT) < flip_tol, eT
 
 
+def test_solve_matches_fp64_oracle_from_identical_state():
+    """dx of the device solve (fp64 elimination) against the fp64 oracle from the same state: the reference's
+    own fp32 `torch.inverse` is the less accurate of the two (cond(H) ~ 1e5)."""
+    c = load_npz("fruit_wild")
+    cfg = zero_eps(cfg_of(c), 1)
+    opt, dec = make_opt(cfg)
+    rd = render_data_of(c)
+    lat = torch.from_numpy(c["init_latent"].copy()).cuda().reshape(1, 32)
+    T = torch.from_numpy(c["init_T_ow"].copy()).cuda().reshape(1, 4, 4)
+    opt.shape_pose_joint_opt_batch(lat, T, [rd], [c["points_w"]], float(c["cube_radius"]), False, max_iter=1)
+    H, b, dx = last_system(dec, 1, 39)
+    tr = O.OptTrace()
+    O.shape_pose_joint_opt(oracle_decoder(np.float64), cfg, c["init_latent"].astype(np.float64), c["init_T_ow"].astype(np.float64),
+                           rd, c["points_w"], float(c["cube_radius"]), False, trace=tr)
+    assert rel(H[0], tr.H[0]) < 1e-4
+    assert rel(b[0], tr.b[0]) < 1e-4
+    assert rel(dx[0], tr.dx[0]) < 1e-3
+    assert rel(lat.cpu().numpy()[0], tr.latent[0]) < 1e-4
+
+
 @pytest.mark.parametrize("var", ["se3", "lmeye", "linocc", "noocc", "gn"])
 def test_config_variants_first_step(var):
     c = load_npz("fruit_wild")
