@@ -76,10 +76,29 @@ struct hm_tc_op {
   int64_t blob_offset;           // byte offset of this op's first stage in the weight blob
 };
 
+// Stage program: the weight stages a tile consumes, flattened on the host into one 32-bit record per ISSUED stage in consumption
+// order (ops F0..F7 first, then B7..B0), so that the MMA issuer, the weight producer and the peer's arrival forwarder walk a flat
+// list instead of re-deriving the plan's nested op / group / part / chunk loops and masks for every stage: the issuing warp's own
+// instruction stream sits on the tile's critical path (measured with the timeline trace, profiles/r02e_trace_*.txt).
+#define HM_TC_REC_CHUNK(r) ((r) & 7u)               // A operand k-chunk of the stage
+#define HM_TC_REC_PART 0x8u                         // 0: lo weight tile (x A_hi), 1: hi weight tile (x A_lo, x A_hi)
+#define HM_TC_REC_GROUP_FIRST 0x10u                 // opens an accumulation group: fresh TMEM buffer, first MMA overwrites
+#define HM_TC_REC_GROUP_LAST 0x20u                  // closes it: the partial accumulator is committed to the epilogue warps
+#define HM_TC_REC_NEED_READY(r) (((r) >> 6) & 7u)   // group opener: A_READY k-step phases that must have been consumed (0..4)
+#define HM_TC_REC_OP_FIRST 0x200u                   // first stage of an op (one A_READY phase per executed op)
+#define HM_TC_REC_OP_LAST 0x400u                    // last stage of an op: the op's remaining A_READY phases are consumed
+#define HM_TC_REC_NARROW 0x800u                     // B0: 64 weight rows per stage (MMA N = 64) instead of 256
+#define HM_TC_REC_OP(r) (((r) >> 12) & 15u)         // op index (timeline trace)
+#define HM_TC_REC_SRC(r) (((r) >> 16) & 0xFFFu)     // blob offset of the stage (both CTAs' halves) in units of 8 KB
+#define HM_TC_REC_GROUP(r) ((r) >> 28)              // group index within the op (timeline trace)
+#define HM_TC_MAX_RECS 480                          // full plan: 4 + 14 x 32 + 16 = 468
+
 struct hm_tc_plan {
   hm_tc_op ops[HM_TC_NOPS_ALL];
   int32_t last_op_fwd, last_op_jac;     // last executed op of a forward-only / forward + gradient pass
   int32_t sparse;                       // 1: some mask is not full, i.e. tiles can fail the checks and need the full plan
+  int32_t n_rec_fwd, n_rec_all;         // stage program: records [0, n_rec_fwd) = forward ops, [n_rec_fwd, n_rec_all) = gradient ops
+  uint32_t rec[HM_TC_MAX_RECS];
 };
 
 struct hm_context {

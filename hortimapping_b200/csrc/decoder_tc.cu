@@ -37,6 +37,8 @@
 // sub-partition, 64 output columns of each half per warp); setmaxnreg moves registers from the control warpgroup to them.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   const uint32_t lead_bars = mapa_rank(bars, 0);                              // the leader's barrier block (cluster address)
   auto lead_bar = [&](int i) { return lead_bars + 8u * i; };
   const int64_t unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
+  const int rec_begin = kBwd ? P.plan.n_rec_fwd : 0, rec_end = kJac ? P.plan.n_rec_all : P.plan.n_rec_fwd;     // this mode's part of the stage program
 #ifdef HM_TESTING
   // timeline of the first CTA pair: (code << 24 | op << 16 | index, clock) pairs; region 0 = MMA issuer, 1 / 2 = first
   // epilogue warp of the leader / peer CTA (scripts/probe_decoder.py trace)
@@ -224,36 +227,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     uint32_t slot = 0, phase = 0;
     long long t_empty = 0;
     for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-      for (int op = kOpBegin; op < kOps; ++op) {
-        const hm_tc_op& o = P.plan.ops[op];
-        const uint32_t gm = o.group_mask;
-        if (gm == 0u) continue;
-        const uint32_t bytes = (uint32_t)o.stage_rows * 128u / CG;     // this CTA's rows of one 64-k fp16 tile
-        const int ng = groups_of(o.n_kchunks, o.n_nblocks);
-        const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
-        const uint8_t* src = P.blob + o.blob_offset + (size_t)rank * bytes;
-        for (int g = 0; g < ng; ++g) {
-          if (!((gm >> g) & 1u)) continue;
-          int step, nh;
-          group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
-          for (int part = 0; part < 2; ++part)
-            for (int which = 0; which < nwhich; ++which) {
-              if (!stage_used(o, step, which)) continue;
-              const int s = (g * 2 + part) * nwhich + which;             // stage index inside the op (consumption order)
-              if (producer) {
-                mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
-                if (elect_one()) {
-                  mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
-                  bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, src + (size_t)s * bytes * CG, bytes, bar(BAR_W_FULL + slot));
-                }
-              } else {
-                mbar_wait(bar(BAR_W_FULL + slot), phase);
-                if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_W_FULL + slot));
-              }
-              __syncwarp();
-              if (++slot == kStages) { slot = 0; phase ^= 1; }
-            }
+      for (int i = rec_begin; i < rec_end; ++i) {
+        const uint32_t r = P.plan.rec[i];
+        const uint32_t bytes = (r & HM_TC_REC_NARROW) ? 64u * 128u / CG : 256u * 128u / CG;      // this CTA's rows of one 64-k fp16 tile
+        if (producer) {
+          mbar_wait_timed<false>(bar(BAR_W_EMPTY + slot), phase ^ 1, t_empty);
+          if (elect_one()) {
+            mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+            bulk_g2s(smem_base + kSmemStages + slot * kStageBytes, P.blob + (size_t)HM_TC_REC_SRC(r) * 8192u + (size_t)rank * bytes, bytes, bar(BAR_W_FULL + slot));
+          }
+        } else {
+          mbar_wait(bar(BAR_W_FULL + slot), phase);
+          if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_W_FULL + slot));
         }
+        __syncwarp();
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
       }
     }
 #ifdef HM_TC_COUNTERS
@@ -265,78 +253,68 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       // and A_hi x W_hi (8 MMAs), each M = 64 per CTA x N = 256 x K = 16, into a FRESH 128-column TMEM buffer (four buffers).
       // The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA), so chains are
       // kept to one group and the epilogue warps add the group partials in fp32 round-to-nearest.
-      uint32_t slot = 0, phase = 0, a_seq = 0, gseq = 0;
+      uint32_t slot = 0, phase = 0, a_seq = 0, gseq = 0, a_par = 0, steps_ready = 0;
       long long t_a = 0, t_part = 0, t_w = 0;
 #ifdef HM_TC_COUNTERS
       const long long t_begin = clock64();
 #endif
+      // descriptors without their address fields; the A chunk / ring slot address is added per stage (16 KB = 1024 units of 16 B)
+      const uint64_t a_desc0 = make_desc(smem_base + kSmemA), w_desc0 = make_desc(smem_base + kSmemStages);
+      constexpr uint32_t idesc_wide = make_idesc(64 * CG, 256), idesc_narrow = make_idesc(64 * CG, 64);
       for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
-        for (int op = kOpBegin; op < kOps; ++op) {
-          const hm_tc_op& o = P.plan.ops[op];
-          const uint32_t gm = o.group_mask;
-          if (gm == 0u) continue;                  // op dropped by the plan: the epilogue warps produce no A operand (and no A_READY phase) for it
-          const uint32_t a_par = a_seq & 1u;       // A_READY completes one phase per executed op
-          ++a_seq;
-          const uint32_t idesc = make_idesc(64 * CG, o.stage_rows);
-          const int ng = groups_of(o.n_kchunks, o.n_nblocks);
-          const int nwhich = (o.n_kchunks == 1) ? 1 : 2;
-          int steps_ready = 0;
-          if (o.n_kchunks == 1) {                  // F0 reads chunk 0 only: its four A_READY phases are consumed up front
-            for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
-            tc_fence_after();
+        uint32_t r_next = P.plan.rec[rec_begin];
+        for (int i = rec_begin; i < rec_end; ++i) {
+          const uint32_t r = r_next;
+          r_next = P.plan.rec[i + 1 < rec_end ? i + 1 : rec_begin];       // (the next record's constant-bank load overlaps this stage)
+          if (r & HM_TC_REC_OP_FIRST) {            // A_READY completes one phase per executed op
+            a_par = a_seq & 1u;
+            ++a_seq;
+            steps_ready = 0;
           }
-          for (int g = 0; g < ng; ++g) {
-            if (!((gm >> g) & 1u)) continue;
-            int step, nh;
-            group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
-            if (steps_ready <= step) {
-              for (; steps_ready <= step; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
+          const uint32_t buf = gseq & (kBufs - 1);
+          if (r & HM_TC_REC_GROUP_FIRST) {
+            const uint32_t need = HM_TC_REC_NEED_READY(r);
+            if (steps_ready < need) {
+              for (; steps_ready < need; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
               tc_fence_after();
             }
-            const uint32_t buf = gseq & (kBufs - 1);
-            if (lane == 0) HM_TRACE(0, 1, op, g);
+            if (lane == 0) HM_TRACE(0, 1, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
             mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq / kBufs) & 1) ^ 1, t_part);
             tc_fence_after();
-            if (lane == 0) HM_TRACE(0, 2, op, g);
-            const uint32_t d = tmem_base + buf * 128;
-            uint32_t fresh = 0u;                                     // the group's first MMA overwrites the buffer
-            const bool two = nwhich == 2 && stage_used(o, step, 0) && stage_used(o, step, 1);
+            if (lane == 0) HM_TRACE(0, 2, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
+          }
+          const uint32_t d = tmem_base + buf * 128;
+          const uint64_t a_hi = a_desc0 + (uint64_t)(HM_TC_REC_CHUNK(r) * (kAChunkBytes >> 4));
+          const uint64_t a_lo = a_hi + (kALoOffset >> 4);
+          const uint64_t w_desc = w_desc0 + (uint64_t)(slot * (kStageBytes >> 4));
+          const uint32_t idesc = (r & HM_TC_REC_NARROW) ? idesc_narrow : idesc_wide;
+          mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(r & HM_TC_REC_PART)) {           // lo weight tile (small terms first); the group's first MMA overwrites the buffer
+              umma_f16<CG>(d, a_hi, w_desc, idesc, (r & HM_TC_REC_GROUP_FIRST) ? 0u : 1u);
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {                   // weight tiles: 0 = lo (small terms first), 1 = hi
-              for (int which = 0; which < nwhich; ++which) {
-                if (!stage_used(o, step, which)) continue;
-                const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
-                const uint64_t a_hi = make_desc(smem_base + kSmemA + chunk * kAChunkBytes);
-                const uint64_t a_lo = a_hi + (kALoOffset >> 4);
-                const uint64_t w_desc = make_desc(smem_base + kSmemStages + slot * kStageBytes);
-                mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
-                tc_fence_after();
-                const bool last = part == 1 && (which == nwhich - 1 || !two);
-                if (elect_one()) {
-                  if (part == 0) {
+              for (int ks = 1; ks < 4; ++ks)       // +32 B per 16-wide k step = +2 in the descriptor's address field
+                umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+            } else {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)                   // +32 B per 16-wide k step = +2 in the descriptor's address field
-                      umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, (fresh | (uint32_t)ks) ? 1u : 0u);
-                  } else {
+              for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_lo + 2 * ks, w_desc + 2 * ks, idesc, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_lo + 2 * ks, w_desc + 2 * ks, idesc, 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
-                  }
-                  umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of the pair
-                  if (last) umma_commit<CG>(bar(BAR_PART_FULL + buf));
-                }
-                fresh = 1u;
-                __syncwarp();
-                if (++slot == kStages) { slot = 0; phase ^= 1; }
-              }
+              for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
             }
+            umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of the pair
+            if (r & HM_TC_REC_GROUP_LAST) umma_commit<CG>(bar(BAR_PART_FULL + buf));
+          }
+          __syncwarp();
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          if (r & HM_TC_REC_GROUP_LAST) {
             ++gseq;
-            if (lane == 0) HM_TRACE(0, 3, op, g);
+            if (lane == 0) HM_TRACE(0, 3, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
           }
           // every executed op completes one phase of all four A_READY barriers (the epilogue warps always publish all k-steps):
           // consume the ones whose groups the plan dropped, so that the phase parity stays in step
-          for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
+          if (r & HM_TC_REC_OP_LAST)
+            for (; steps_ready < 4; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
         }
       }
 #ifdef HM_TC_COUNTERS
@@ -861,6 +839,40 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
   plan.last_op_jac = cut ? 11 : 15;
   plan.sparse = 0;
   for (int l = 0; l < 8; ++l) plan.sparse |= (amask[l] != 0xFF);
+  // ---- stage program (common.cuh): one record per issued stage, in the order the blob stores them
+  int n = 0;
+  plan.n_rec_fwd = 0;
+  for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
+    if (op == HM_TC_NOPS_FWD) plan.n_rec_fwd = n;
+    const hm_tc_op& o = plan.ops[op];
+    if (o.group_mask == 0) continue;
+    const int ng = groups_of(o.n_kchunks, o.n_nblocks), nwhich = (o.n_kchunks == 1) ? 1 : 2;
+    const int op_begin = n;
+    for (int g = 0; g < ng; ++g) {
+      if (!((o.group_mask >> g) & 1u)) continue;
+      int step, nh;
+      group_of(o.n_kchunks, o.n_nblocks, g, step, nh);
+      const int group_begin = n;
+      for (int part = 0; part < 2; ++part)
+        for (int which = 0; which < nwhich; ++which) {
+          const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+          if (!((o.chunk_mask >> chunk) & 1u)) continue;
+          const int sidx = (g * 2 + part) * nwhich + which;               // stage index inside the op (blob order)
+          const int64_t off = o.blob_offset + (int64_t)sidx * o.stage_rows * 128;
+          uint32_t r = (uint32_t)chunk | (part ? HM_TC_REC_PART : 0u) | (o.stage_rows == 64 ? HM_TC_REC_NARROW : 0u) | ((uint32_t)op << 12) |
+                       ((uint32_t)(off / 8192) << 16) | ((uint32_t)g << 28);
+          if (off % 8192 != 0 || off / 8192 > 0xFFF || n >= HM_TC_MAX_RECS) { fprintf(stderr, "hm_tc: stage program overflow\n"); abort(); }
+          plan.rec[n++] = r;
+        }
+      // the group opener waits for the A operand's k-steps up to its own (F0 reads chunk 0 only: all four phases up front)
+      plan.rec[group_begin] |= HM_TC_REC_GROUP_FIRST | ((uint32_t)(o.n_kchunks == 1 ? 4 : step + 1) << 6);
+      plan.rec[n - 1] |= HM_TC_REC_GROUP_LAST;
+    }
+    plan.rec[op_begin] |= HM_TC_REC_OP_FIRST;
+    plan.rec[n - 1] |= HM_TC_REC_OP_LAST;
+  }
+  plan.n_rec_all = n;
+  for (int i = n; i < HM_TC_MAX_RECS; ++i) plan.rec[i] = 0;
 }
 
 }  // namespace

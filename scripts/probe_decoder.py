@@ -85,7 +85,7 @@ def main():
             lat1, xyz1 = t[0, :32].contiguous(), t[:, 32:].contiguous()
             run = lambda: dec.sdf_jacobian(lat1, xyz1)
         else:
-            run = lambda: dec._eval_rows(t, with_jac=True)
+            run = lambda: dec._eval_rows(t, with_jac=not os.environ.get("PROBE_FWD"))     # PROBE_FWD=1: forward-only launch
         run()
         torch.cuda.synchronize()
         L.hm_debug_tc_trace(dec.handle, 1, None)
@@ -94,7 +94,7 @@ def main():
         out = np.zeros(3 * 8192 * 2, np.uint32)
         L.hm_debug_tc_trace(dec.handle, 0, out.ctypes.data)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        np.save(os.path.join(ROOT, "gpurun_out", "trace.npy"), out.reshape(3, 8192, 2))
+        np.save(os.path.join(ROOT, "gpurun_out", os.environ.get("PROBE_OUT", "trace.npy")), out.reshape(3, 8192, 2))
         print("trace saved", [int((out.reshape(3, 8192, 2)[r, :, 0] != 0).sum()) for r in range(3)])
     elif what == "pair":
         for m_rows, n_cols in ((64, 256), (128, 256), (64, 64)):
