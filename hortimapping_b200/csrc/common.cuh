@@ -84,7 +84,7 @@ struct hm_tc_op {
 #define HM_TC_REC_PART 0x8u                         // 0: lo weight tile (x A_hi), 1: hi weight tile (x A_lo, x A_hi)
 #define HM_TC_REC_GROUP_FIRST 0x10u                 // opens an accumulation group: fresh TMEM buffer, first MMA overwrites
 #define HM_TC_REC_GROUP_LAST 0x20u                  // closes it: the partial accumulator is committed to the epilogue warps
-#define HM_TC_REC_NEED_READY(r) (((r) >> 6) & 7u)   // group opener: A_READY k-step phases that must have been consumed (0..4)
+#define HM_TC_REC_NEED_READY(r) (((r) >> 6) & 7u)   // group opener: A_READY k-step phases that must have been consumed (0..4); 7 = F0: X0_READY
 #define HM_TC_REC_OP_FIRST 0x200u                   // first stage of an op (one A_READY phase per executed op)
 #define HM_TC_REC_OP_LAST 0x400u                    // last stage of an op: the op's remaining A_READY phases are consumed
 #define HM_TC_REC_NARROW 0x800u                     // B0: 64 weight rows per stage (MMA N = 64) instead of 256
@@ -97,6 +97,9 @@ struct hm_tc_plan {
   hm_tc_op ops[HM_TC_NOPS_ALL];
   int32_t last_op_fwd, last_op_jac;     // last executed op of a forward-only / forward + gradient pass
   int32_t sparse;                       // 1: some mask is not full, i.e. tiles can fail the checks and need the full plan
+  int32_t x0_chunk;                     // A chunk that holds F0's operand [x0 * s | 0 ...] (K padded 35 -> 64)
+  int32_t x0_early;                     // 1: that chunk is free while the tile's LAST op runs (forward-only and forward + gradient passes), so the
+                                        // next tile's operand is written there and F0's MMAs follow the last op's without a bubble
   int32_t n_rec_fwd, n_rec_all;         // stage program: records [0, n_rec_fwd) = forward ops, [n_rec_fwd, n_rec_all) = gradient ops
   uint32_t rec[HM_TC_MAX_RECS];
 };

@@ -67,7 +67,7 @@ constexpr int kMaskWordsPerOp = 64 * 16;           // 64 points x 512 bits per f
 
 // barrier slots (8 bytes each) inside the 256-byte control block at kSmemBars, followed by a few control words
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = kMaxStages, BAR_A_READY = 2 * kMaxStages, BAR_PART_FULL = BAR_A_READY + 4,
-       BAR_PART_EMPTY = BAR_PART_FULL + 4, BAR_COUNT = BAR_PART_EMPTY + 4 };
+       BAR_PART_EMPTY = BAR_PART_FULL + 4, BAR_X0_READY = BAR_PART_EMPTY + 4, BAR_COUNT = BAR_X0_READY + 1 };
 constexpr int kCtlTmemPtr = 8 * BAR_COUNT;         // TMEM base column written by tcgen05.alloc
 constexpr int kCtlViolated = kCtlTmemPtr + 4;      // set by an epilogue warp whose tile contradicted the sparse plan
 static_assert(kCtlViolated + 4 <= 256, "control block overflows into the bias / dot-product scratch");
@@ -119,12 +119,6 @@ __host__ __device__ __forceinline__ void group_of(int n_kchunks, int n_nblocks, 
   if (n_kchunks == 1) { step = 0; nh = g; }
   else if (n_nblocks == 1) { step = g; nh = 0; }
   else { step = (0x32321100u >> (4 * g)) & 0xF; nh = (0xCAu >> g) & 1; }
-}
-
-// Sparse plan (common.cuh hm_tc_op): is stage (step, which) of an op multiplied?
-__device__ __forceinline__ bool stage_used(const hm_tc_op& o, int step, int which) {
-  const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
-  return (o.chunk_mask >> chunk) & 1u;
 }
 
 // The kernel runs as clusters of two CTAs (one TPC).  Each CTA owns a tile of 64 points; the pair issues cta_group::2 MMAs
@@ -187,15 +181,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       ++trace_n;
     }
   };
+#define HM_TRACE_OP(...) trace(__VA_ARGS__)          // one event per op (MMA issuer): cheap enough to leave the timing alone
+#ifdef HM_TC_LIGHT
+#define HM_TRACE(...) ((void)0)
+#else
 #define HM_TRACE(...) trace(__VA_ARGS__)
+#endif
 #else
 #define HM_TRACE(...) ((void)0)
+#define HM_TRACE_OP(...) ((void)0)
 #endif
 
   if (threadIdx.x == 0) {
     // W_FULL of the leader also collects the peer's "my half has landed" arrive
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_W_FULL + s), rank == 0 ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
     for (int p = 0; p < 4; ++p) mbar_init(bar(BAR_A_READY + p), kEpiWarps * CG / 2);      // a k-step's chunks come from half of the warps
+    mbar_init(bar(BAR_X0_READY), kEpiWarps * CG);                                          // F0's operand: every warp writes 8 of its 64 columns
     for (int b = 0; b < kBufs; ++b) { mbar_init(bar(BAR_PART_FULL + b), 1); mbar_init(bar(BAR_PART_EMPTY + b), kEpiWarps * CG); }
     ctl[kCtlViolated / 4] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,6 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (lane == 0 && (warp == 1 || warp == kCtrlWarps)) HM_TRACE(warp == 1 ? 0 : 1 + rank, 0, 0, 0);     // common time origin
+#ifdef HM_TESTING
+  const long long t_cta_begin = clock64();
+#endif
 
   if (!kRedo && blockIdx.x == 0 && threadIdx.x == 0) {     // exact row / tile accounting for the roofline (rows actually evaluated)
     atomicAdd(reinterpret_cast<unsigned long long*>(P.flags + (kBwd ? HM_TC_FLAG_ROWS_BWD : kJac ? HM_TC_FLAG_ROWS_JAC : HM_TC_FLAG_ROWS_FWD)), (unsigned long long)n_rows);
@@ -248,12 +252,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     if (producer && rank == 0 && lane == 0) atomicAdd((unsigned long long*)(P.flags + HM_TC_FLAG_DEBUG + 0), (unsigned long long)t_empty);
 #endif
   } else if (warp == 1) {
-      // ===================== MMA issuer (leader CTA; whole warp walks the loops, one elected lane issues) =====================
+      // ===================== MMA issuer (leader CTA; the whole warp walks the stage program, one elected lane issues) =====================
       // One accumulation group = (k-step = 2 k-chunks, 256-column output half): per chunk A_hi x W_lo (4 MMAs), then A_lo x W_hi
       // and A_hi x W_hi (8 MMAs), each M = 64 per CTA x N = 256 x K = 16, into a FRESH 128-column TMEM buffer (four buffers).
       // The tensor core accumulates fp32 with round-toward-zero (measured: -1e-7 relative per chained MMA), so chains are
       // kept to one group and the epilogue warps add the group partials in fp32 round-to-nearest.
-      uint32_t slot = 0, phase = 0, a_seq = 0, gseq = 0, a_par = 0, steps_ready = 0;
+      uint32_t slot = 0, phase = 0, a_seq = 0, x_seq = 0, gseq = 0, a_par = 0, steps_ready = 0;
       long long t_a = 0, t_part = 0, t_w = 0;
 #ifdef HM_TC_COUNTERS
       const long long t_begin = clock64();
@@ -266,51 +270,60 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         for (int i = rec_begin; i < rec_end; ++i) {
           const uint32_t r = r_next;
           r_next = P.plan.rec[i + 1 < rec_end ? i + 1 : rec_begin];       // (the next record's constant-bank load overlaps this stage)
-          if (r & HM_TC_REC_OP_FIRST) {            // A_READY completes one phase per executed op
-            a_par = a_seq & 1u;
-            ++a_seq;
-            steps_ready = 0;
-          }
-          const uint32_t buf = gseq & (kBufs - 1);
-          if (r & HM_TC_REC_GROUP_FIRST) {
-            const uint32_t need = HM_TC_REC_NEED_READY(r);
-            if (steps_ready < need) {
-              for (; steps_ready < need; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
+          if (r & HM_TC_REC_OP_FIRST) {
+            if (HM_TC_REC_NEED_READY(r) == 7u) {   // F0: its operand has a barrier of its own, one phase per tile (it may have been
+              steps_ready = 7;                     // written while the previous tile's last op ran); no A_READY phase is consumed
+              mbar_wait_timed<kPair>(bar(BAR_X0_READY), x_seq & 1u, t_a);
+              ++x_seq;
               tc_fence_after();
+            } else {                               // A_READY completes one phase per executed op
+              a_par = a_seq & 1u;
+              ++a_seq;
+              steps_ready = 0;
             }
-            if (lane == 0) HM_TRACE(0, 1, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
-            mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq / kBufs) & 1) ^ 1, t_part);
+          }
+          {
+            const uint32_t buf = gseq & (kBufs - 1);
+            if (r & HM_TC_REC_GROUP_FIRST) {
+              const uint32_t need = HM_TC_REC_NEED_READY(r);
+              if (steps_ready < need) {
+                for (; steps_ready < need; ++steps_ready) mbar_wait_timed<kPair>(bar(BAR_A_READY + steps_ready), a_par, t_a);
+                tc_fence_after();
+              }
+              if (lane == 0) HM_TRACE(0, 1, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
+              mbar_wait_timed<kPair>(bar(BAR_PART_EMPTY + buf), ((gseq / kBufs) & 1) ^ 1, t_part);
+              tc_fence_after();
+              if (lane == 0) HM_TRACE(0, 2, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
+            }
+            const uint32_t d = tmem_base + buf * 128;
+            const uint64_t a_hi = a_desc0 + (uint64_t)(HM_TC_REC_CHUNK(r) * (kAChunkBytes >> 4));
+            const uint64_t a_lo = a_hi + (kALoOffset >> 4);
+            const uint64_t w_desc = w_desc0 + (uint64_t)(slot * (kStageBytes >> 4));
+            const uint32_t idesc = (r & HM_TC_REC_NARROW) ? idesc_narrow : idesc_wide;
+            mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
             tc_fence_after();
-            if (lane == 0) HM_TRACE(0, 2, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
-          }
-          const uint32_t d = tmem_base + buf * 128;
-          const uint64_t a_hi = a_desc0 + (uint64_t)(HM_TC_REC_CHUNK(r) * (kAChunkBytes >> 4));
-          const uint64_t a_lo = a_hi + (kALoOffset >> 4);
-          const uint64_t w_desc = w_desc0 + (uint64_t)(slot * (kStageBytes >> 4));
-          const uint32_t idesc = (r & HM_TC_REC_NARROW) ? idesc_narrow : idesc_wide;
-          mbar_wait_timed<kPair>(bar(BAR_W_FULL + slot), phase, t_w);
-          tc_fence_after();
-          if (elect_one()) {
-            if (!(r & HM_TC_REC_PART)) {           // lo weight tile (small terms first); the group's first MMA overwrites the buffer
-              umma_f16<CG>(d, a_hi, w_desc, idesc, (r & HM_TC_REC_GROUP_FIRST) ? 0u : 1u);
+            if (elect_one()) {
+              if (!(r & HM_TC_REC_PART)) {           // lo weight tile (small terms first); the group's first MMA overwrites the buffer
+                umma_f16<CG>(d, a_hi, w_desc, idesc, (r & HM_TC_REC_GROUP_FIRST) ? 0u : 1u);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks)       // +32 B per 16-wide k step = +2 in the descriptor's address field
-                umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
-            } else {
+                for (int ks = 1; ks < 4; ++ks)       // +32 B per 16-wide k step = +2 in the descriptor's address field
+                  umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+              } else {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_lo + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_lo + 2 * ks, w_desc + 2 * ks, idesc, 1u);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks) umma_f16<CG>(d, a_hi + 2 * ks, w_desc + 2 * ks, idesc, 1u);
+              }
+              umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of the pair
+              if (r & HM_TC_REC_GROUP_LAST) umma_commit<CG>(bar(BAR_PART_FULL + buf));
             }
-            umma_commit<CG>(bar(BAR_W_EMPTY + slot));          // frees the slot in both CTAs of the pair
-            if (r & HM_TC_REC_GROUP_LAST) umma_commit<CG>(bar(BAR_PART_FULL + buf));
+            __syncwarp();
+            if (r & HM_TC_REC_GROUP_LAST) {
+              if (lane == 0) HM_TRACE(0, 3, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
+            }
           }
-          __syncwarp();
           if (++slot == kStages) { slot = 0; phase ^= 1; }
-          if (r & HM_TC_REC_GROUP_LAST) {
-            ++gseq;
-            if (lane == 0) HM_TRACE(0, 3, HM_TC_REC_OP(r), HM_TC_REC_GROUP(r));
-          }
+          if (r & HM_TC_REC_GROUP_LAST) ++gseq;
           // every executed op completes one phase of all four A_READY barriers (the epilogue warps always publish all k-steps):
           // consume the ones whose groups the plan dropped, so that the phase parity stays in step
           if (r & HM_TC_REC_OP_LAST)
@@ -394,6 +407,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       return __ldg(P.xyz + lr * 3 + c);
     };
     auto latent_row_of = [&](int64_t lr) -> int32_t { return (!P.rows && P.row_latent) ? __ldg(P.row_latent + lr) : 0; };
+    // A operand of F0: chunk x0_chunk = [x0 * s, 0 ...] (K padded 35 -> 64) of row lr; column group g8 writes k in [8*g8, +8).
+    // Published on X0_READY (all 16 warps of both CTAs arrive once per tile).
+    bool x0_written = false;
+    int sat_next = 0;                            // saturation seen while writing the NEXT tile's operand (attributed to that tile's fruit)
+    auto write_x0 = [&](int64_t lr_x, const float* lat_x, int& sat_x) {
+      const float s0 = P.plan.ops[0].in_scale;
+      float xin[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xin[i] = 0.f;
+      if (g8 < 4) {                              // 8 independent loads: one memory latency, not eight
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xin[i] = __ldg(lat_x + 8 * g8 + i);
+      } else if (g8 == 4) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xin[c] = xyz_of(lr_x, c);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) store_pair(smem, P.plan.x0_chunk, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat_x);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_bar(BAR_X0_READY));
+    };
     int32_t cur_li = (unit0 < n_units) ? latent_row_of(row_of(tile_of(unit0))) : 0, nxt_li = 0;
     for (int64_t unit = unit0; unit < n_units; unit += unit_stride) {
       const int64_t tile = tile_of(unit);
@@ -408,22 +443,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
       const uint32_t* mask_rd = my_masks;
       if (kMode == 0 && P.mask_out && tile >= 0) mask_wr = P.mask_out + (size_t)tile * 8 * kMaskStride + (size_t)(e_w * 32 + lane) * 2;
       if constexpr (!kBwd) {
-      // ---- A operand of F0: chunk 0 = [x0 * s, 0 ...] (K padded 35 -> 64); column group g8 writes k in [8*g8, +8)
-        const float s0 = P.plan.ops[0].in_scale;
-        float xin[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xin[i] = 0.f;
-        if (g8 < 4) {                            // 8 independent loads: one memory latency, not eight
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xin[i] = __ldg(lat_ptr + 8 * g8 + i);
-        } else if (g8 == 4) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) xin[c] = xyz_of(lr, c);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) store_pair(smem, 0, p, 8 * g8 + 2 * e, xin[2 * e] * s0, xin[2 * e + 1] * s0, sat);
-        publish(cq >> 1);                        // every warp arrives once per k-step of its own chunks' parity (see finalize)
-        publish(2 + (cq >> 1));
+        // ---- A operand of F0 (unless it was written while the previous tile's last op ran, see below)
+        if (!x0_written) write_x0(lr, lat_ptr, sat);
+        x0_written = false;
       } else {
         // ---- backward-only tile: the masks of this thread's point sit where the forward-only pass stored them -- in the slot of
         //      the thread that owned the SAME column group of that point there (sub-partition 2 * hq + point / 32, lane point % 32)
@@ -476,11 +498,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const bool narrow = (o.stage_rows == 64);        // B0: 64 output columns (32 TMEM columns), one group per step
         const bool wide = (o.n_kchunks != 1);
         const bool fwd_op = op < 8;
-        if (!kBwd && op == last_op && unit + unit_stride < n_units) {      // next tile: latent-table row now, x0 lines into L2
+        if (!kBwd && op == last_op && unit + unit_stride < n_units) {
+          // next tile.  If F0's operand chunk is free during this op (plan.x0_early) it is written NOW -- every reader of that chunk in
+          // this tile has completed (all earlier ops' partials have been promoted) and this op's epilogue writes no A operand -- so
+          // that F0's MMAs follow this op's MMAs directly and the tile hand-over (final epilogue, SDF / Jacobian stores, input loads)
+          // leaves the op chain's critical path.  Otherwise: latent-table row now, x0 lines into L2.
           const int64_t nr = row_of(tile_of(unit + unit_stride));
           nxt_li = latent_row_of(nr);
-          if (!P.rows && P.grid_n == 0 && g8 == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.xyz + nr * 3));
-          if (P.rows && g8 <= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rows + nr * HM_IN + 8 * g8));
+          if (P.plan.x0_early) {
+            write_x0(nr, lat_ptr_of(nr, nxt_li), sat_next);
+            x0_written = true;
+          } else {
+            if (!P.rows && P.grid_n == 0 && g8 == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.xyz + nr * 3));
+            if (P.rows && g8 <= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rows + nr * HM_IN + 8 * g8));
+          }
         }
         // which of this thread's two column blocks the epilogue has to produce (all of them for a forward op: its ReLU bits are the
         // check of the plan's assumptions; for a backward op only the columns somebody reads)
@@ -508,6 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #endif
           tc_fence_after();
           if (e_w == 0 && lane == 0) HM_TRACE(1 + rank, 10, op, gseq & 0xffff);
+#ifdef HM_TC_LIGHT
+          if constexpr (first && nh == 0) { if (e_w == 0 && lane == 0) HM_TRACE_OP(1 + rank, 10, op, gseq & 0xffff); }
+#endif
           auto release = [&]() {               // all TMEM reads of this buffer are complete
             tc_fence_before();
             __syncwarp();
@@ -751,6 +785,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         sat = 0;
         sat2 = 0u;
       }
+      sat = sat_next;
+      sat_next = 0;
       if (!kRedo && P.plan.sparse) {
         if (__any_sync(0xffffffffu, viol) && lane == 0) ctl[kCtlViolated / 4] = 1u;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -770,6 +806,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     }
 #endif
   }
+#ifdef HM_TESTING
+  // per-CTA busy time of the launch (role loops only), parked behind the peer's timeline region: how evenly the statically
+  // assigned tiles finish across the grid (scripts/probe_decoder.py trace prints min / mean / max)
+  if (P.trace != nullptr && !kRedo && threadIdx.x == kCtrlWarps * 32 && blockIdx.x < 1024)
+    P.trace[((size_t)2 * kTraceCap + kTraceCap / 2 + blockIdx.x) * 2 + 1] = (uint32_t)(clock64() - t_cta_begin);
+#endif
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();        // the peer's TMEM / shared memory stay valid until both CTAs are done
@@ -837,6 +879,17 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
   for (int op = 0; op < 8; ++op) plan.ops[op].need_out = plan.ops[op + 1].chunk_mask;      // (op 7 feeds B7; ignored by forward-only passes)
   plan.last_op_fwd = 7;
   plan.last_op_jac = cut ? 11 : 15;
+  // F0's operand goes to a chunk nobody reads while the LAST op of a tile runs (either kind of pass), if there is one: the next
+  // tile's operand is then written during that op and F0's MMAs are issued right behind it (kernel: X0_READY)
+  {
+    const uint8_t busy = (uint8_t)(plan.ops[7].chunk_mask | plan.ops[plan.last_op_jac].chunk_mask);
+    plan.x0_chunk = 0;
+    plan.x0_early = 0;
+    const int pref[8] = {5, 6, 4, 3, 7, 2, 1, 0};
+    if (!getenv("HM_TC_NO_X0_EARLY"))
+      for (int c : pref)
+        if (!((busy >> c) & 1u)) { plan.x0_chunk = c; plan.x0_early = 1; break; }
+  }
   plan.sparse = 0;
   for (int l = 0; l < 8; ++l) plan.sparse |= (amask[l] != 0xFF);
   // ---- stage program (common.cuh): one record per issued stage, in the order the blob stores them
@@ -855,8 +908,9 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
       const int group_begin = n;
       for (int part = 0; part < 2; ++part)
         for (int which = 0; which < nwhich; ++which) {
-          const int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
+          int chunk = (o.n_kchunks == 1) ? 0 : chunk_of(step, which);
           if (!((o.chunk_mask >> chunk) & 1u)) continue;
+          if (op == 0) chunk = plan.x0_chunk;                              // where the A operand of F0 lives (fill_plan_masks)
           const int sidx = (g * 2 + part) * nwhich + which;               // stage index inside the op (blob order)
           const int64_t off = o.blob_offset + (int64_t)sidx * o.stage_rows * 128;
           uint32_t r = (uint32_t)chunk | (part ? HM_TC_REC_PART : 0u) | (o.stage_rows == 64 ? HM_TC_REC_NARROW : 0u) | ((uint32_t)op << 12) |
@@ -865,7 +919,8 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
           plan.rec[n++] = r;
         }
       // the group opener waits for the A operand's k-steps up to its own (F0 reads chunk 0 only: all four phases up front)
-      plan.rec[group_begin] |= HM_TC_REC_GROUP_FIRST | ((uint32_t)(o.n_kchunks == 1 ? 4 : step + 1) << 6);
+      const uint32_t need_ready = op == 0 ? (g == 0 ? 7u : 0u) : (uint32_t)step + 1u;      // F0: X0_READY (waited once, at the op's first stage)
+      plan.rec[group_begin] |= HM_TC_REC_GROUP_FIRST | (need_ready << 6);
       plan.rec[n - 1] |= HM_TC_REC_GROUP_LAST;
     }
     plan.rec[op_begin] |= HM_TC_REC_OP_FIRST;

@@ -7,9 +7,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
-#ifdef HM_TESTING
+#if defined(HM_TESTING) && !defined(HM_TC_LIGHT)
 #define HM_TC_COUNTERS 1      // the testing build keeps per-role wait-cycle counters (hm_debug_tc_wait_cycles)
-#endif
+#endif                        // (-DHM_TC_LIGHT: a testing build whose only instrumentation is one timeline event per op)
 
 namespace hm_tc {
 

@@ -61,6 +61,14 @@ def main():
                   f"({N * 7.34208e6 / j / 1e9:.0f} TFLOP/s)  re-evaluated tiles {c1['tiles_redone_forward'] - c0['tiles_redone_forward']}/{c1['tiles_forward'] - c0['tiles_forward']} fwd, "
                   f"{c1['tiles_redone_jacobian'] - c0['tiles_redone_jacobian']}/{c1['tiles_jacobian'] - c0['tiles_jacobian']} jac")
         return
+    if what == "sweep":                        # ms per decode call against the number of rows: fixed cost of a call vs cost per tile
+        from hortimapping_b200.decoder import Decoder
+        dec = calibrated(Decoder(W, b), codes)
+        for n in (9472, 18944, 66304, 132608, 265216, 1060864):          # multiples of 148 x 64 rows: whole rounds of tiles
+            tt = torch.from_numpy(make_rows(codes, n)).cuda()
+            f, j = ms_of(lambda: dec._eval_rows(tt, with_jac=False)), ms_of(lambda: dec._eval_rows(tt, with_jac=True))
+            print(f"rows {n:8d} ({n // 9472:3d} tiles per CTA): forward {f:.4f} ms  forward+gradient {j:.4f} ms")
+        return
     dec = calibrated(_testing.testing_decoder(W, b), codes)
     L = _testing.lib()
     if what == "wait":
@@ -96,6 +104,10 @@ def main():
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.save(os.path.join(ROOT, "gpurun_out", os.environ.get("PROBE_OUT", "trace.npy")), out.reshape(3, 8192, 2))
         print("trace saved", [int((out.reshape(3, 8192, 2)[r, :, 0] != 0).sum()) for r in range(3)])
+        busy = out.reshape(3, 8192, 2)[2, 4096:4096 + 148, 1].astype(np.int64)          # per-CTA busy cycles of the traced launch
+        if busy.any():
+            print("per-CTA busy cycles: min %d  mean %.0f  max %d   (leaders %s ...)" % (busy.min(), busy.mean(), busy.max(), busy[0:16:2].tolist()))
+            np.save(os.path.join(ROOT, "gpurun_out", "cta_busy_" + os.environ.get("PROBE_OUT", "trace.npy")), busy)
     elif what == "pair":
         for m_rows, n_cols in ((64, 256), (128, 256), (64, 64)):
             A = np.zeros((2, m_rows, 64), np.float16)

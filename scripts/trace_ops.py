@@ -3,15 +3,18 @@ when the MMA warp began waiting for each op's first A operand -> duration of eve
 import sys
 import numpy as np
 tr = np.load(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/trace.npy')
-w, c = tr[0, :, 0].astype(np.int64), tr[0, :, 1].astype(np.int64)
+# default: the MMA issuer's "A ready" events (region 0, code 1); a -DHM_TC_LIGHT build only records the leader CTA's first epilogue
+# warp seeing the first partial accumulator of each op (region 1, code 10): `trace_ops.py file 1 10`
+REGION, CODE = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (0, 1)
+w, c = tr[REGION, :, 0].astype(np.int64), tr[REGION, :, 1].astype(np.int64)
 n = int(np.nonzero(w)[0].max()) + 1
 d = np.diff(c[:n]); d[d < 0] += 1 << 32
 t = np.concatenate([[0], np.cumsum(d)])
 starts = []            # (time, op) of the first "A ready" wait of each op occurrence
 prev_op = -1
-for i in range(1, n):
+for i in range(0, n):
     code, op = w[i] >> 24, (w[i] >> 16) & 0xff
-    if code == 1 and op != prev_op:
+    if code == CODE and op != prev_op:
         starts.append((int(t[i]), int(op)))
         prev_op = op
 units, cur = [], []
