@@ -121,8 +121,10 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         busy = sorted(sm)[len(sm) // 2:] if sm else []
+        pw = sorted(float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit())
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw[len(pw) // 2:]) if pw else None}      # board power under load (the box runs at its 1000 W cap)
 
 
 def product_sdf_jac(dec):

@@ -575,7 +575,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
 #endif
           if (e_w == 0 && lane == 0) HM_TRACE(1 + rank, 13, opx, nh);
           const int col0 = col0_of(nh);
-          const bool emit = nh ? emit1 : emit0;                 // does the next op multiply this thread's chunk?
+          // Skip concat (deep_sdf_decoder.py:87-88): columns 480..511 of lin4's input are x0[3..34].  The eight threads that own
+          // point p (one per column group g8) each load four of them -- ONE round trip to L2 at the start of lin3's last finalize,
+          // hidden under its ReLU loop -- and write them into chunk 7 below; the thread that owns those columns of lin3's (padded,
+          // all-zero) output does not emit them.  (A single thread loading all 32 values serialised the loads under register
+          // pressure: lin3 + lin4 took 12 k / 21 k cycles of a forward / forward + gradient tile against 3 k of MMA work.)
+          const bool skip_cols = nh == 1 && opx == 3;
+          float xs[4] = {0.f, 0.f, 0.f, 0.f};
+          if (skip_cols) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 3 + 4 * g8 + i;
+              xs[i] = j < HM_LATENT ? __ldg(lat_ptr + j) : xyz_of(lr, j - HM_LATENT);
+            }
+          }
+          const bool emit = (nh ? emit1 : emit0) && !(skip_cols && hq == 1 && cq == 3);      // does the next op multiply this thread's chunk?
           const bool may_live = (o.verify_alive >> (4 * nh + chunk_lo)) & 1u;      // may this thread's chunk hold non-zeros (forward ops)?
           if (opx < 7) {
             // ---------------- forward hidden layer: h = relu(acc + b); next A = h * s_next (bias pre-scaled by s_next)
@@ -596,23 +610,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               }
               if (emit) emit_unit(nh, u, r);
             }
+            if (skip_cols) {
+              // columns 480..511 of lin4's input = x0[3..34]: this thread's four values (loaded above), two fp16 pairs of point p
+              store_pair(smem, 7, p, 32 + 4 * g8, xs[0] * s_next_x, xs[1] * s_next_x, sat);
+              store_pair(smem, 7, p, 34 + 4 * g8, xs[2] * s_next_x, xs[3] * s_next_x, sat);
+            }
             if (nh == 1 && opx == 3 && hq == 1 && cq >= 2) {
               // lin3 has 477 outputs; columns 477..511 of the next input are the raw x0 (skip concat, deep_sdf_decoder.py:87-88).
               // Kept out of the loop above (a branch per element would end its instruction-level parallelism): the threads that
-              // own columns >= 477 rewrite those units and clear their ReLU bits.  (Chunk 7 is always read by lin4.)
-              if (cq == 3) {                           // columns 480..511 = x0[3..34]: 29 latent values + xyz, loaded as one batch
-                float xv[32];
-#pragma unroll
-                for (int j = 0; j < 29; ++j) xv[j] = __ldg(lat_ptr + 3 + j);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) xv[29 + c] = xyz_of(lr, c);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  float r[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) r[i] = xv[8 * u + i] * s_next_x;
-                  emit_unit(nh, u, r);
-                }
+              // own columns >= 477 clear their ReLU bits.  (Chunk 7 is always read by lin4.)
+              if (cq == 3) {                           // columns 480..511: written by the point's eight threads (skip_cols)
                 m_ = 0u;
               } else {                                 // columns 448..479: 472..476 are the last lin3 outputs, 477..479 = x0[0..2]
                 float r[8];
