@@ -100,6 +100,9 @@ struct hm_tc_plan {
   int32_t x0_chunk;                     // A chunk that holds F0's operand [x0 * s | 0 ...] (K padded 35 -> 64)
   int32_t x0_early;                     // 1: that chunk is free while the tile's LAST op runs (forward-only and forward + gradient passes), so the
                                         // next tile's operand is written there and F0's MMAs follow the last op's without a bubble
+  int32_t mask_layers;                  // bit l: the gradient pass reads the ReLU bits of h_l (l = 0..6), i.e. B_{l+1} is executed and is not the last op
+  int32_t mask_chunk;                   // forward + gradient pass: A chunk that no op touches between the first stored layer and the last reader and
+                                        // that holds those bits (<= 4 layers x 4 KB) instead of the global scratch; -1 = none (full plan)
   int32_t n_rec_fwd, n_rec_all;         // stage program: records [0, n_rec_fwd) = forward ops, [n_rec_fwd, n_rec_all) = gradient ops
   uint32_t rec[HM_TC_MAX_RECS];
 };

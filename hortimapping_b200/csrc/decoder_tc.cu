@@ -356,6 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
     const uint32_t t_addr = tmem_base + ((uint32_t)(32 * sp) << 16) + 32 * cq;
     uint32_t* my_masks = P.masks + ((size_t)blockIdx.x * 8 * kEpiWarps * 32 + (size_t)(e_w * 32 + lane)) * 2;   // [op][thread][2 words]
     constexpr size_t kMaskStride = (size_t)kEpiWarps * 32 * 2;
+    // this thread's slot in the plan's shared-memory mask chunk: [layer slot][thread] x 8 bytes (forward + gradient pass)
+    uint8_t* const mask_smem = smem + kSmemA + (uint32_t)(P.plan.mask_chunk < 0 ? 0 : P.plan.mask_chunk) * kAChunkBytes + (uint32_t)(e_w * 32 + lane) * 8u;
     uint32_t gseq = 0;
     int sat = 0;
 #ifdef HM_TC_COUNTERS
@@ -520,7 +522,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         const bool emit0 = (need >> chunk_lo) & 1u, emit1 = (need >> (4 + chunk_lo)) & 1u;
         m0 = m1 = 0u;
         if (kJac && op >= 8 && op < 15 && !o.is_last) {
-          const uint2 mw = *reinterpret_cast<const uint2*>(mask_rd + (size_t)(14 - op) * kMaskStride);   // ReLU mask of h_{l-1}, l = 15 - op
+          // ReLU mask of h_{l-1}, l = 15 - op
+          const uint2 mw = (kMode == 1 && P.plan.mask_chunk >= 0)
+                               ? *reinterpret_cast<const uint2*>(mask_smem + 4096u * (uint32_t)__popc(P.plan.mask_layers & ((1u << (14 - op)) - 1u)))
+                               : *reinterpret_cast<const uint2*>(mask_rd + (size_t)(14 - op) * kMaskStride);
           m0 = mw.x; m1 = mw.y;
         }
         // collect the partial accumulator of one (step, n-half) group.  FIRST: the group opens the op for this output half
@@ -550,6 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           if ((narrow && cq != 0) || !(nh ? need1 : need0)) {      // B0's 64 output columns occupy TMEM columns 0..31 only; unread columns are skipped
             release();
           } else {
+#ifdef HM_TC_PROMOTE32
             float v[32];
             tmem_ld32_nowait(t_addr + buf * 128, v);
             tmem_ld_wait_dep32(v);
@@ -559,6 +565,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
               const float2 w = make_float2(v[2 * i], v[2 * i + 1]);
               if constexpr (first) acc[nh][i] = w; else acc[nh][i] = add2(acc[nh][i], w);
             }
+#else
+            // two 16-column halves: 16 live registers next to the 64 accumulators instead of 32 (the kernel has no L1 to speak of
+            // -- 227 KB of the SM's 256 KB are shared memory -- so every spilled register is an L2 round trip on the op chain)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v[16];
+              tmem_ld16_nowait(t_addr + buf * 128 + 16 * h, v);
+              tmem_ld_wait_dep16(v);
+              if (h == 1) release();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 w = make_float2(v[2 * i], v[2 * i + 1]);
+                if constexpr (first) acc[nh][8 * h + i] = w; else acc[nh][8 * h + i] = add2(acc[nh][8 * h + i], w);
+              }
+            }
+#endif
           }
           ++gseq;
 #ifdef HM_TC_COUNTERS
@@ -751,7 +773,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             if (gm & 128u) promote(I1, I0);
           }
           finalize(I1, op, k_mul, unscale, s_next, m1);
-          if ((kMode == 1 && op < 7) || (kMode == 0 && P.mask_out && op < 8)) *reinterpret_cast<uint2*>(mask_wr + (size_t)op * kMaskStride) = make_uint2(m0, m1);
+          // ReLU bits of this layer.  Forward + gradient pass: only the layers the plan's gradient ops read, and into the plan's free A
+          // chunk when it has one (the thread that writes them reads them back; no global store next to the proxy fences).
+          if (kMode == 1 && op < 7 && ((P.plan.mask_layers >> op) & 1)) {
+            if (P.plan.mask_chunk >= 0) *reinterpret_cast<uint2*>(mask_smem + 4096u * (uint32_t)__popc(P.plan.mask_layers & ((1u << op) - 1u))) = make_uint2(m0, m1);
+            else *reinterpret_cast<uint2*>(mask_wr + (size_t)op * kMaskStride) = make_uint2(m0, m1);
+          }
+          if (kMode == 0 && P.mask_out && op < 8) *reinterpret_cast<uint2*>(mask_wr + (size_t)op * kMaskStride) = make_uint2(m0, m1);
         }
         // ---- lin8 + tanh (deep_sdf_decoder.py:107-108): every thread sums the 8 column-group partials of its point.  A forward-only
         //      pass does it at the end of F7 (= the end of the tile).  With the gradient requested it is DEFERRED to the end of B7's
@@ -899,6 +927,21 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
   }
   plan.sparse = 0;
   for (int l = 0; l < 8; ++l) plan.sparse |= (amask[l] != 0xFF);
+  // ReLU bits the gradient pass reads, and a shared-memory home for them.  A global (or local) store in the op loop is expensive
+  // here: fence.proxy.async -- two per op -- is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, i.e. it waits for the store's round trip to L2.
+  plan.mask_layers = 0;
+  for (int l = 0; l < 7; ++l) {
+    const hm_tc_op& b = plan.ops[14 - l];            // B_{l+1}: d_l = (d_{l+1} W_{l+1}) * relu'(h_l)
+    if (b.group_mask != 0 && !b.is_last) plan.mask_layers |= 1 << l;
+  }
+  plan.mask_chunk = -1;
+  if (plan.mask_layers != 0 && __builtin_popcount(plan.mask_layers) <= 4 && !getenv("HM_TC_NO_SMEM_MASKS")) {
+    const int first_l = __builtin_ctz(plan.mask_layers);
+    uint8_t touched = (uint8_t)(1u << plan.x0_chunk);
+    for (int op = first_l; op <= 14 - first_l; ++op) touched |= (uint8_t)(plan.ops[op].chunk_mask | (plan.ops[op].group_mask ? plan.ops[op].need_out : 0));
+    for (int c = 6; c >= 0; --c)
+      if (!((touched >> c) & 1u)) { plan.mask_chunk = c; break; }
+  }
   // ---- stage program (common.cuh): one record per issued stage, in the order the blob stores them
   int n = 0;
   plan.n_rec_fwd = 0;
