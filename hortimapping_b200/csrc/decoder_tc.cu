@@ -29,6 +29,10 @@
 //   * three modes (template kMode): forward only (optionally storing every row's ReLU bits, 512 B per row), forward + gradient,
 //     and gradient ONLY from stored bits + SDF values (the joint loop differentiates a subset of the rows it has just evaluated,
 //     loss.py:185-215; the second forward evaluation the reference pays for them is not needed).
+//   * the MMA issuer, the weight producer and the peer's arrival forwarder walk a flat STAGE PROGRAM (hm_tc_plan::rec, one 32-bit
+//     record per issued weight stage, built on the host): the issuing warp's instruction stream is on the tile's critical path.
+//     F0's operand has a barrier of its own (X0_READY) and, when the plan leaves a chunk unread during the tile's last op, is
+//     written for the NEXT tile while that op runs, so F0's MMAs follow the last op's directly.
 //   * lin8's weight and the eight bias vectors travel in the kernel-parameter constant bank: every lane of an epilogue warp reads
 //     the same columns, so they arrive at register speed without shared-memory staging or barriers.
 //
@@ -773,8 +777,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
             if (gm & 128u) promote(I1, I0);
           }
           finalize(I1, op, k_mul, unscale, s_next, m1);
-          // ReLU bits of this layer.  Forward + gradient pass: only the layers the plan's gradient ops read, and into the plan's free A
-          // chunk when it has one (the thread that writes them reads them back; no global store next to the proxy fences).
+          // ReLU bits of this layer.  Forward + gradient pass: only the layers the plan's gradient ops read (a plan that ends the
+          // gradient pass at lin4 reads three of the seven: tile 116 k -> 108 k cycles together with the two-half promotion), and into
+          // the plan's free A chunk when it has one -- the thread that writes them reads them back.  (Measured on one box: the
+          // shared-memory home and the global scratch take the same time; the store itself is not what a layer costs.)
           if (kMode == 1 && op < 7 && ((P.plan.mask_layers >> op) & 1)) {
             if (P.plan.mask_chunk >= 0) *reinterpret_cast<uint2*>(mask_smem + 4096u * (uint32_t)__popc(P.plan.mask_layers & ((1u << op) - 1u))) = make_uint2(m0, m1);
             else *reinterpret_cast<uint2*>(mask_wr + (size_t)op * kMaskStride) = make_uint2(m0, m1);
@@ -927,8 +933,7 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
   }
   plan.sparse = 0;
   for (int l = 0; l < 8; ++l) plan.sparse |= (amask[l] != 0xFF);
-  // ReLU bits the gradient pass reads, and a shared-memory home for them.  A global (or local) store in the op loop is expensive
-  // here: fence.proxy.async -- two per op -- is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, i.e. it waits for the store's round trip to L2.
+  // ReLU bits the gradient pass reads, and a shared-memory home for them (kernel: mask_smem)
   plan.mask_layers = 0;
   for (int l = 0; l < 7; ++l) {
     const hm_tc_op& b = plan.ops[14 - l];            // B_{l+1}: d_l = (d_{l+1} W_{l+1}) * relu'(h_l)

@@ -383,3 +383,69 @@ def test_fp16_saturation_is_attributed_per_fruit_and_underflow_is_bounded():
     y_ref = O.DecoderOracle(W, b, (4,), np.float64).forward(tiny.astype(np.float64))
     np.testing.assert_allclose(y.cpu().numpy().reshape(-1), y_ref.reshape(-1), rtol=1e-4, atol=2e-6)
     assert dec.saturation_count() == 0
+
+
+def test_plan_variants_are_bit_identical_over_many_tiles_per_cta():
+    """The plan decides where two things live: F0's operand (written for the NEXT tile during the tile's last op when a chunk is
+    free, HM_TC_NO_X0_EARLY switches that off) and the ReLU bits of the forward + gradient pass (the plan's free A chunk, or the
+    global scratch with HM_TC_NO_SMEM_MASKS).  Neither may change a bit of the output.  Several tiles per CTA and a ragged tail, so
+    that the tile hand-over and the chunk reuse across tiles are exercised; forward-only, forward + gradient, and the
+    per-fruit latent-table input mode the optimisers use."""
+    import os
+    from hortimapping_b200.decoder import Decoder, calibration_rows
+    from tests.helpers import pepper_weights
+    W, b, codes = pepper_weights()
+    n = 148 * 64 * 5 + 77
+    g = np.random.default_rng(5)
+    rows = np.concatenate([codes[g.integers(0, codes.shape[0], n)], ((g.random((n, 3)) * 2 - 1) * 0.06).astype(np.float32)], 1)
+    t = torch.from_numpy(rows).cuda()
+    cal = calibration_rows(codes, 0.15, n=int(os.environ.get("HM_TEST_CAL_ROWS", "65536")))
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update({k: "1" for k in env})
+        try:
+            dec = Decoder(W, b)            # the plan is built (and the switches are read) when the engine is calibrated
+            dec.calibrate(cal)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        f, _ = dec._eval_rows(t, with_jac=False)
+        y, j = dec._eval_rows(t, with_jac=True)
+        y1, j1 = dec.sdf_jacobian(t[0, :32].contiguous(), t[:, 32:].contiguous())
+        return f, y, j, y1, j1
+
+    base = run(())
+    assert torch.equal(base[0], base[1])
+    for env in (("HM_TC_NO_X0_EARLY",), ("HM_TC_NO_SMEM_MASKS",), ("HM_TC_NO_X0_EARLY", "HM_TC_NO_SMEM_MASKS")):
+        other = run(env)
+        for a, o in zip(base, other):
+            assert torch.equal(a, o), env
+
+
+def test_testing_library_decoder_is_the_product_decoder():
+    """The TEST-ONLY library compiles the same kernels with timeline / wait-cycle instrumentation.  Different register allocation and
+    timing, same protocol: its forward-only and forward + gradient launches over many tiles per CTA must finish and give the
+    product's bits (a protocol that only works for one instruction schedule shows up here, scripts/check_testing_decoder.py)."""
+    import os
+    from hortimapping_b200 import _testing
+    from hortimapping_b200.decoder import calibration_rows
+    from tests.gpu_helpers import pepper_decoder
+    from tests.helpers import pepper_weights
+    W, b, codes = pepper_weights()
+    ref = pepper_decoder()
+    dec = _testing.testing_decoder(W, b)
+    dec.calibrate(calibration_rows(codes, 0.15, n=int(os.environ.get("HM_TEST_CAL_ROWS", "262144"))))
+    n = 148 * 64 * 6 + 5
+    g = np.random.default_rng(11)
+    rows = np.concatenate([codes[g.integers(0, codes.shape[0], n)], ((g.random((n, 3)) * 2 - 1) * 0.05).astype(np.float32)], 1)
+    t = torch.from_numpy(rows).cuda()
+    for jac in (False, True):
+        a, r = dec._eval_rows(t, with_jac=jac), ref._eval_rows(t, with_jac=jac)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], r[0])
+        if jac:
+            assert torch.equal(a[1], r[1])
