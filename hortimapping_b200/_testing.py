@@ -14,7 +14,7 @@ from . import _lib
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhortimapping_b200_testing.so")
 DEBUG_EXPORTS = ["hm_debug_exp_pose", "hm_debug_huber_w2", "hm_debug_tc_selftest", "hm_debug_tc_wait_cycles", "hm_debug_tc_trace",
-                 "hm_debug_tc_mma_rate", "hm_debug_tc_pair_probe", "hm_debug_tc_ingest"]
+                 "hm_debug_tc_mma_rate", "hm_debug_tc_pair_probe", "hm_debug_tc_ingest", "hm_debug_tc_plan"]
 _tlib = None
 
 
@@ -32,6 +32,7 @@ def lib() -> C.CDLL:
         L.hm_debug_tc_mma_rate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.hm_debug_tc_pair_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.hm_debug_tc_ingest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.hm_debug_tc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]      # host only: no context, no GPU
         _tlib = L
     return _tlib
 

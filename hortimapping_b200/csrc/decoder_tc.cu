@@ -985,7 +985,49 @@ void fill_plan_masks(hm_tc_plan& plan, const uint8_t (&amask)[8]) {
   for (int i = n; i < HM_TC_MAX_RECS; ++i) plan.rec[i] = 0;
 }
 
+// geometry of the 16 ops and where each op's stages start in the weight blob (all stages of all groups, lo tiles and hi tiles,
+// whether a plan issues them or not); returns the blob size
+int64_t plan_geometry(hm_tc_plan& plan) {
+  int64_t bytes = 0;
+  for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
+    hm_tc_op& o = plan.ops[op];
+    o.n_kchunks = (op == 0) ? 1 : 8;
+    o.n_nblocks = (op == 15) ? 1 : 2;                // 256-column output halves (B0: one 64-column block)
+    o.stage_rows = (op == 15) ? 64 : 256;
+    o.blob_offset = bytes;
+    bytes += (int64_t)groups_of(o.n_kchunks, o.n_nblocks) * 2 * (o.n_kchunks == 1 ? 1 : 2) * o.stage_rows * 128;
+  }
+  return bytes;
+}
+
 }  // namespace
+
+#ifdef HM_TESTING
+// TEST-ONLY, host only (no context, no GPU): the plan the engine would build for the given per-layer alive-chunk masks --
+// masks, stage program, chunk assignments -- so that tests/test_host_logic.py can re-derive it independently.
+// out_ops[op] = {n_kchunks, n_nblocks, stage_rows / 64, chunk_mask, half_mask, group_mask, need_out, verify_alive, is_last};
+// out_info = {n_rec_fwd, n_rec_all, last_op_fwd, last_op_jac, sparse, x0_chunk, x0_early, mask_layers, mask_chunk}.
+extern "C" int hm_debug_tc_plan(const uint8_t* amask8, int32_t* out_info, uint32_t* out_rec, uint8_t* out_ops, int64_t* out_blob_offset) {
+  hm_tc_plan plan;
+  memset(&plan, 0, sizeof(plan));
+  plan_geometry(plan);
+  uint8_t am[8];
+  memcpy(am, amask8, 8);
+  fill_plan_masks(plan, am);
+  const int32_t info[9] = {plan.n_rec_fwd, plan.n_rec_all, plan.last_op_fwd, plan.last_op_jac, plan.sparse, plan.x0_chunk, plan.x0_early,
+                           plan.mask_layers, plan.mask_chunk};
+  memcpy(out_info, info, sizeof(info));
+  memcpy(out_rec, plan.rec, sizeof(plan.rec));
+  for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
+    const hm_tc_op& o = plan.ops[op];
+    const uint8_t v[9] = {(uint8_t)o.n_kchunks, (uint8_t)o.n_nblocks, (uint8_t)(o.stage_rows / 64), o.chunk_mask, o.half_mask, o.group_mask, o.need_out,
+                          o.verify_alive, o.is_last};
+    memcpy(out_ops + 9 * op, v, 9);
+    out_blob_offset[op] = o.blob_offset;
+  }
+  return HM_OK;
+}
+#endif
 
 static int hm_tc_blob_copies() {
   const char* e = getenv("HM_TC_BLOB_COPIES");
@@ -1037,7 +1079,9 @@ int hm_tc_init(hm_context* ctx) {
   }
   // op list: F0..F7 (lin0..lin7), B7..B1, B0
   hm_tc_plan& plan = ctx->tc_plan;
+  const int64_t blob_total = plan_geometry(plan);
   std::vector<uint8_t> blob;
+  blob.reserve((size_t)blob_total);
   auto wmax = [&](int l) {
     float m = 0.f;
     for (float v : Wp[l]) m = std::max(m, std::fabs(v));
@@ -1046,15 +1090,12 @@ int hm_tc_init(hm_context* ctx) {
   for (int op = 0; op < HM_TC_NOPS_ALL; ++op) {
     const bool fwd = op < 8;
     const int l = fwd ? op : 15 - op;
-    hm_tc_op& o = plan.ops[op];
-    o.n_kchunks = (op == 0) ? 1 : 8;
-    o.n_nblocks = (op == 15) ? 1 : 2;                // 256-column output halves (B0: one 64-column block)
-    o.stage_rows = (op == 15) ? 64 : 256;
+    hm_tc_op& o = plan.ops[op];                      // (geometry and blob offsets: plan_geometry)
     const float amax = std::max(ctx->act_absmax[op], 1e-20f);
     o.in_scale = pow2_floor(1024.f / amax);          // 64x headroom below the fp16 maximum
     const float w_scale = pow2_floor(8192.f / wmax(l));
     o.out_unscale = 1.f / (o.in_scale * w_scale);
-    o.blob_offset = (int64_t)blob.size();
+    HM_CHECK(o.blob_offset == (int64_t)blob.size(), "tensor-core blob layout out of step with plan_geometry");
     const std::vector<float>& W = Wp[l];
     const int in_dim = ctx->in_dim[l];
     const size_t tile_bytes = (size_t)o.stage_rows * 128;

@@ -217,3 +217,106 @@ def test_calibration_rows_cover_the_optimisers_working_region():
     r_codes = np.linalg.norm(codes - mean, axis=1).max()
     assert np.linalg.norm(z - mean, axis=1).max() < r_codes + 0.03 * 6 * np.sqrt(32)
     assert np.linalg.norm(z[1024:] - mean, axis=1).mean() < np.linalg.norm(z[:1024] - mean, axis=1).mean()
+
+
+# ---------------------------------------------------------------- tensor-core engine: the plan and its stage program (host logic)
+def _tc_plan(amask):
+    import ctypes as C
+    from hortimapping_b200 import _testing
+    L = _testing.lib()
+    info, rec = np.zeros(9, np.int32), np.zeros(480, np.uint32)
+    ops, off = np.zeros((16, 9), np.uint8), np.zeros(16, np.int64)
+    am = np.asarray(amask, np.uint8)
+    assert L.hm_debug_tc_plan(am.ctypes.data, info.ctypes.data, rec.ctypes.data, ops.ctypes.data, off.ctypes.data) == 0
+    keys = ("n_rec_fwd", "n_rec_all", "last_op_fwd", "last_op_jac", "sparse", "x0_chunk", "x0_early", "mask_layers", "mask_chunk")
+    return dict(zip(keys, (int(v) for v in info))), rec, ops, off
+
+
+def _groups(n_kchunks, n_nblocks):
+    """(step, half) of the accumulation groups of an op in issue order."""
+    if n_kchunks == 1:
+        return [(0, g) for g in range(n_nblocks)]
+    if n_nblocks == 1:
+        return [(g, 0) for g in range(4)]
+    return [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (3, 0), (2, 1), (3, 1)]
+
+
+def _chunk_of(step, which):
+    return (step & 1) + 4 * (step >> 1) + 2 * which
+
+
+@pytest.mark.parametrize("amask", [
+    [0xFF] * 8,                                                   # a model without dead units: the full plan
+    [0xFF, 0x05, 0x01, 0x00, 0x1F, 0x1F, 0x07, 0x05],             # sweetpepper_32: 8 / 2 / 1 / 0 / 5 / 5 / 3 / 2 alive chunks, lin3 dead
+    [0x7F, 0x0F, 0x05, 0x00, 0x3F, 0xFF, 0x0F, 0x01],             # lin3 dead, a layer that needs all eight chunks after it
+    [0x1F, 0x07, 0x05, 0xFF, 0x1F, 0x05, 0x07, 0x05],             # sparse, lin3 alive: the gradient pass runs down to lin0
+])
+def test_tc_stage_program_is_the_plan_flattened(amask):
+    """hm_tc_plan::rec (what the MMA issuer, the weight producer and the peer's forwarder walk) re-derived from the plan's masks:
+    every issued stage once, in blob order, with the right A chunk, flags, A_READY requirement and blob offset; and the plan's
+    chunk assignments (F0 operand, ReLU-bit home) never collide with a chunk some op of the window touches."""
+    info, rec, ops, off = _tc_plan(amask)
+    cut = amask[3] == 0
+    assert info["last_op_fwd"] == 7 and info["last_op_jac"] == (11 if cut else 15)
+    assert info["sparse"] == int(any(m != 0xFF for m in amask))
+    want, n_fwd = [], None
+    for op in range(16):
+        if op == 8:
+            n_fwd = len(want)
+        nk, nb, rows64, cmask, hmask, gmask, need_out, valive, is_last = (int(v) for v in ops[op])
+        assert (nk, nb, rows64) == ((1 if op == 0 else 8), (1 if op == 15 else 2), (1 if op == 15 else 4))
+        groups = _groups(nk, nb)
+        nwhich = 1 if nk == 1 else 2
+        # the group mask is what the chunk / half masks imply
+        for g, (step, nh) in enumerate(groups):
+            chunks = [0] if nk == 1 else [_chunk_of(step, 0), _chunk_of(step, 1)]
+            assert bool((gmask >> g) & 1) == bool(((hmask >> nh) & 1) and any((cmask >> c) & 1 for c in chunks))
+        first_of_op = True
+        stages_of_op = []
+        for g, (step, nh) in enumerate(groups):
+            if not (gmask >> g) & 1:
+                continue
+            st = []
+            for part in range(2):
+                for which in range(nwhich):
+                    chunk = 0 if nk == 1 else _chunk_of(step, which)
+                    if not (cmask >> chunk) & 1:
+                        continue
+                    sidx = (g * 2 + part) * nwhich + which
+                    st.append(dict(op=op, g=g, chunk=(info["x0_chunk"] if op == 0 else chunk), part=part, narrow=rows64 == 1,
+                                   src=(int(off[op]) + sidx * rows64 * 64 * 128) // 8192, first=False, last=False, need=0))
+            st[0]["first"], st[-1]["last"] = True, True
+            st[0]["need"] = (7 if g == 0 else 0) if op == 0 else step + 1
+            assert st[0]["part"] == 0                              # the group's first MMA (which overwrites the buffer) is a lo-tile MMA
+            stages_of_op += st
+        if stages_of_op:
+            stages_of_op[0]["op_first"], stages_of_op[-1]["op_last"] = True, True
+        want += stages_of_op
+    assert info["n_rec_fwd"] == n_fwd and info["n_rec_all"] == len(want) <= 480
+    for r, w in zip(rec[:len(want)], want):
+        r = int(r)
+        got = dict(chunk=r & 7, part=(r >> 3) & 1, first=bool(r & 0x10), last=bool(r & 0x20), need=(r >> 6) & 7, op_first=bool(r & 0x200),
+                   op_last=bool(r & 0x400), narrow=bool(r & 0x800), op=(r >> 12) & 15, src=(r >> 16) & 0xFFF, g=r >> 28)
+        for k, v in got.items():
+            assert v == w.get(k, False), (k, got, w)
+    assert not rec[len(want):].any()
+    # blob offsets: every stage of every group, lo and hi tiles, issued or not
+    assert int(off[0]) == 0 and all(int(off[op + 1]) - int(off[op]) == (4 if op == 0 else 32) * 256 * 128 for op in range(15))
+    # F0's operand chunk: free during the last op of a forward-only pass and of a forward + gradient pass, or chunk 0 / written at the tile start
+    busy = int(ops[7][3]) | int(ops[info["last_op_jac"]][3])
+    if info["x0_early"]:
+        assert not (busy >> info["x0_chunk"]) & 1
+    else:
+        assert busy == 0xFF and info["x0_chunk"] == 0
+    # ReLU bits the gradient pass reads, and their shared-memory home
+    layers = [l for l in range(7) if int(ops[14 - l][5]) != 0 and not int(ops[14 - l][8])]
+    assert info["mask_layers"] == sum(1 << l for l in layers)
+    if info["mask_chunk"] >= 0:
+        assert 0 < len(layers) <= 4 and info["mask_chunk"] != info["x0_chunk"]
+        for op in range(min(layers), 14 - min(layers) + 1):
+            touched = int(ops[op][3]) | (int(ops[op][6]) if int(ops[op][5]) else 0)
+            assert not (touched >> info["mask_chunk"]) & 1, op
+    if amask == [0xFF] * 8:
+        assert info["mask_chunk"] == -1 and info["mask_layers"] == 0x7F and not info["x0_early"]
+    if cut:
+        assert layers == [4, 5, 6]
