@@ -121,7 +121,6 @@ struct hm_context {
   // tensor-core engine
   uint8_t* d_tc_blob = nullptr;    // pre-swizzled fp16 hi/lo weight stages for all 16 ops
   size_t tc_blob_bytes = 0;
-  int tc_blob_copies = 1;
   hm_tc_plan tc_plan;              // the sparse plan (== the full plan for a model without dead units)
   hm_tc_plan tc_plan_full;         // every mask full: the reference evaluation, used for the tiles that fail the sparse plan's checks
   int32_t* d_tc_redo = nullptr;    // [0] = number of queued tiles, [4 ..] = their indices (grow-only)

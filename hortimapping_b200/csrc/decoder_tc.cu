@@ -79,8 +79,6 @@ static_assert(kCtlViolated + 4 <= 256, "control block overflows into the bias / 
 struct TcParams {
   hm_tc_plan plan;
   const uint8_t* blob;
-  int64_t blob_bytes;         // size of one copy of the weight blob
-  int32_t blob_copies;        // copies laid out back to back (CTAs spread over them)
   float b8;                   // lin8 bias
   const float* rows;          // [n][35] or null
   const float* xyz;           // [n][3]
@@ -1029,12 +1027,6 @@ extern "C" int hm_debug_tc_plan(const uint8_t* amask8, int32_t* out_info, uint32
 }
 #endif
 
-static int hm_tc_blob_copies() {
-  const char* e = getenv("HM_TC_BLOB_COPIES");
-  int c = e ? atoi(e) : 1;
-  return c < 1 ? 1 : (c > 8 ? 8 : c);
-}
-
 int hm_tc_init(hm_context* ctx) {
   // ---- which hidden units were alive in the calibration pass -> unit permutation + chunk masks
   // perm[l][new] = old index of the unit that sits at position `new` of layer l in the tensor-core engine's order
@@ -1123,14 +1115,11 @@ int hm_tc_init(hm_context* ctx) {
   ctx->tc_plan_full = plan;
   fill_plan_masks(ctx->tc_plan, amask);
   fill_plan_masks(ctx->tc_plan_full, afull);
-  const int copies = hm_tc_blob_copies();
   if (ctx->d_tc_blob) HM_CUDA(cudaDeviceSynchronize());      // re-calibration: no kernel on any stream may still read the old blob / biases
-  if (ctx->d_tc_blob && (ctx->tc_blob_bytes != blob.size() || ctx->tc_blob_copies != copies)) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
-  if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size() * copies));
+  if (ctx->d_tc_blob && ctx->tc_blob_bytes != blob.size()) { cudaFree(ctx->d_tc_blob); ctx->d_tc_blob = nullptr; }
+  if (!ctx->d_tc_blob) HM_CUDA(cudaMalloc(&ctx->d_tc_blob, blob.size()));
   ctx->tc_blob_bytes = blob.size();
-  ctx->tc_blob_copies = copies;
-  for (int c = 0; c < copies; ++c)
-    HM_CUDA(cudaMemcpy(ctx->d_tc_blob + (size_t)c * blob.size(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  HM_CUDA(cudaMemcpy(ctx->d_tc_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   if (!ctx->d_tc_masks) {
     HM_CUDA(cudaMalloc(&ctx->d_tc_masks, sizeof(uint32_t) * (size_t)ctx->sm_count * 8 * kMaskWordsPerOp));
     HM_CUDA(cudaMalloc(&ctx->d_tc_flags, sizeof(int32_t) * HM_TC_FLAG_COUNT));
@@ -1200,8 +1189,6 @@ int hm_tc_decode(hm_context* ctx, const hm_rows& rows, float* d_sdf, float* d_ja
   TcParams P;
   P.plan = ctx->sparse_plan ? ctx->tc_plan : ctx->tc_plan_full;
   P.blob = ctx->d_tc_blob;
-  P.blob_bytes = (int64_t)ctx->tc_blob_bytes;
-  P.blob_copies = ctx->tc_blob_copies;
   memcpy(P.bias, ctx->h_tc_bias.data(), sizeof(P.bias));
   memcpy(P.w8, ctx->h_w8p, sizeof(P.w8));
   P.b8 = ctx->h_b[8][0];
