@@ -790,8 +790,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
         //      epilogue: nothing needs the SDF or tanh' before the last gradient op, and here it would sit between F7's last finalize
         //      and B7's first promotion, i.e. on the critical path of the op chain; there it runs while the tensor core works on B6.
         if ((kMode == 0 && op == 7) || (kMode == 1 && op == 8)) {
-          // (no barrier in front of the writes: every warp has read the previous tile's sums before it published that tile's first A
-          // operand, and no warp gets past its first promotion of this tile before all of them have published)
+          // (no barrier in front of the writes: a warp reads the previous tile's sums before it leaves that tile -- before the
+          // tile-end barrier of a sparse pass, or, without one, before it publishes any A operand of lin0's output -- and no warp
+          // gets to this point of the next tile earlier: lin1 multiplies every chunk the plan keeps of h0, i.e. waits for all warps)
           dot_scratch[p * 8 + g8] = dot;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           const float4 d0 = *reinterpret_cast<const float4*>(dot_scratch + p * 8), d1 = *reinterpret_cast<const float4*>(dot_scratch + p * 8 + 4);
