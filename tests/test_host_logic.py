@@ -320,3 +320,37 @@ def test_tc_stage_program_is_the_plan_flattened(amask):
         assert info["mask_chunk"] == -1 and info["mask_layers"] == 0x7F and not info["x0_early"]
     if cut:
         assert layers == [4, 5, 6]
+
+
+@pytest.mark.parametrize("model", ["sweetpepper_32", "strawberry_32"])
+def test_shipped_models_get_the_fast_plan(model):
+    """Both shipped DeepSDF models, calibrated on the product's own calibration rows (alive sets measured here with the fp32 oracle,
+    on the device with the CUDA-core engine): lin3 is dead, so the gradient pass ends at lin4 and reads the ReLU bits of lin4..6
+    only; the plan has a free chunk for the next tile's F0 operand; the issued tensor work is well below the dense count."""
+    from hortimapping_b200.decoder import calibration_rows
+    from oracle import hm_oracle as O
+    z = load_npz(model)
+    W, b = [z[f"W{l}"] for l in range(9)], [z[f"b{l}"] for l in range(9)]
+    rows = calibration_rows(z["latent_codes"], 0.15, n=16384).numpy()
+    _, (masks, _) = O.DecoderOracle(W, b, (4,), np.float32).forward(rows, return_cache=True)
+    alive = [int(np.asarray(m).any(0).sum()) for m in masks[:8]]
+    assert alive[3] == 0 and all(a > 0 for i, a in enumerate(alive) if i != 3), alive
+    fill = [0, 2, 1, 3, 4, 6, 5, 7]                    # chunk fill order of the alive-first unit permutation (decoder_tc.cu kChunkFill)
+    amask = []
+    for l, a in enumerate(alive):
+        c = 0 if l == 3 else max(1, -(-a // 64))
+        amask.append(sum(1 << fill[i] for i in range(c)))
+    info, rec, ops, off = _tc_plan(amask)
+    assert info["sparse"] == 1 and info["last_op_jac"] == 11
+    assert info["x0_early"] == 1 and info["mask_layers"] == 0b1110000
+    # sweetpepper_32 leaves a chunk free for the ReLU bits of lin4..6; strawberry_32's lin4 keeps six chunks alive, its bits go to the
+    # global scratch (same time, DESIGN.md 4.1)
+    assert (info["mask_chunk"] >= 0) == (model == "sweetpepper_32"), (info, amask)
+    # issued fp16 tensor work per row: every record is a (lo | hi) stage of 4 | 8 MMAs of 128 rows x stage_rows x 16
+    def flop(lo, hi):
+        return sum((8 if (int(r) >> 3) & 1 else 4) * 2.0 * (64 if int(r) & 0x800 else 256) * 16 for r in rec[lo:hi])
+    fwd, jac = flop(0, info["n_rec_fwd"]), flop(0, info["n_rec_all"])
+    dense_fwd = 3.0 * 2 * (64 * 512 + 7 * 512 * 512)          # three fp16 products per fp32 product, K of lin0 padded to 64
+    assert fwd < 0.6 * dense_fwd and fwd < jac < 2.2 * fwd, (fwd, jac, dense_fwd)
+    if model == "sweetpepper_32":
+        assert [bin(m).count("1") for m in amask] == [8, 2, 1, 0, 5, 5, 3, 2] or sum(bin(m).count("1") for m in amask) <= 26, amask
