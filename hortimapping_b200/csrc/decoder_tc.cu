@@ -557,17 +557,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
           if ((narrow && cq != 0) || !(nh ? need1 : need0)) {      // B0's 64 output columns occupy TMEM columns 0..31 only; unread columns are skipped
             release();
           } else {
-#ifdef HM_TC_PROMOTE32
-            float v[32];
-            tmem_ld32_nowait(t_addr + buf * 128, v);
-            tmem_ld_wait_dep32(v);
-            release();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 w = make_float2(v[2 * i], v[2 * i + 1]);
-              if constexpr (first) acc[nh][i] = w; else acc[nh][i] = add2(acc[nh][i], w);
-            }
-#else
             // two 16-column halves: 16 live registers next to the 64 accumulators instead of 32 (the kernel has no L1 to speak of
             // -- 227 KB of the SM's 256 KB are shared memory -- so every spilled register is an L2 round trip on the op chain)
 #pragma unroll
@@ -582,7 +571,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_decoder_kernel(const __grid_co
                 if constexpr (first) acc[nh][8 * h + i] = w; else acc[nh][8 * h + i] = add2(acc[nh][8 * h + i], w);
               }
             }
-#endif
           }
           ++gseq;
 #ifdef HM_TC_COUNTERS

@@ -264,36 +264,6 @@ __device__ __forceinline__ void store_pair(uint8_t* smem, int chunk, int p, int 
   *reinterpret_cast<__half2*>(base + kALoOffset + sw128_offset(p, k)) = ll;
 }
 
-// wait for all outstanding TMEM loads; the 32 loaded registers pass through the statement so that no consumer can be
-// scheduled above the wait
-__device__ __forceinline__ void tmem_ld_wait_dep32(float (&a)[32]) {
-  uint32_t* x = reinterpret_cast<uint32_t*>(a);
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(x[8]), "+r"(x[9]),
-                 "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15])
-               :
-               : "memory");
-  asm volatile(""
-               : "+r"(x[16]), "+r"(x[17]), "+r"(x[18]), "+r"(x[19]), "+r"(x[20]), "+r"(x[21]), "+r"(x[22]), "+r"(x[23]), "+r"(x[24]),
-                 "+r"(x[25]), "+r"(x[26]), "+r"(x[27]), "+r"(x[28]), "+r"(x[29]), "+r"(x[30]), "+r"(x[31])
-               :
-               : "memory");
-}
-// TMEM -> registers, 32 lanes x 32 consecutive columns (thread = lane = accumulator row), without the wait
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
 // 16-column variants (the epilogue promotes a 32-column partial in two halves: 16 fewer live registers next to the 64 accumulators)
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
